@@ -1,0 +1,194 @@
+/*
+ * openfly_b200 -- C ABI of the B200-native force-evaluation path for openFLY.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types. The C++20 shim in
+ * include/openfly_b200/fly.hpp re-creates the reference's class surface (fly::potential::Generic,
+ * fly::neigh::List, fly::minimise::LBFGS, fly::saddle::Dimer) on top of these entry points, and
+ * openfly_b200/capi.py binds the same symbols through ctypes for the tests and bench.py.
+ *
+ * Reference interfaces replaced (paths relative to the openFLY tree):
+ *   ofly_tables_*          potential::DataEAM            src/potential/EAM/data.cpp:67-153,
+ *                                                        include/libfly/potential/EAM/data.hpp:59-116
+ *   ofly_neigh_*           neigh::List                   include/libfly/neigh/list.hpp:86-161, src/neigh/list.cpp:37-165
+ *   ofly_eam_*             potential::Generic / EAM      include/libfly/potential/generic.hpp:79-136, src/potential/EAM/eam.cpp:33-233
+ *   ofly_lbfgs_minimise    minimise::LBFGS::minimise     include/libfly/minimise/LBFGS/lbfgs.hpp:96-118, src/minimise/LBFGS/lbfgs.cpp:29-115
+ *   ofly_dimer_find_sp     saddle::Dimer::find_sp        include/libfly/saddle/dimer.hpp:107-155, src/saddle/dimer.cpp:28-171
+ *                          (+ saddle::Rotor::eff_gradient src/saddle/rotor.cpp:49-164)
+ *
+ * Data layout at the boundary is the reference's: every vector property is one contiguous
+ * double[3N] with xyz interleaved per atom (include/libfly/system/adaptor.hpp:70-78); TypeID is
+ * uint32[N]; Frozen is one byte per atom. A "batch" is R independent replicas of one N-atom
+ * system (same box, types and frozen flags -- what saddle::Master::find_batch launches,
+ * src/saddle/find.cpp:684-755); batched arrays are [R][3N], replica-major.
+ *
+ * Every call returns an ofly_status. Errors never abort: device-side faults (table overrun,
+ * neighbour-capacity overflow) are recorded per replica and reported by the call that saw them.
+ * Pointers named *_host are host memory, *_dev are device memory on the context's device.
+ */
+#ifndef OPENFLY_B200_H
+#define OPENFLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ofly_status {
+  OFLY_OK = 0,
+  OFLY_ERR_INVALID = 1,       /* contract violation: fly::RuntimeError in the reference (core.hpp:89-138) */
+  OFLY_ERR_OUT_OF_BOUNDS = 2, /* Spline::OutOfBounds (include/libfly/utility/spline.hpp:46-51): recoverable */
+  OFLY_ERR_CUDA = 3,          /* CUDA runtime failure */
+  OFLY_ERR_CAPACITY = 4       /* an internal buffer bound was exceeded even after regrowing */
+} ofly_status;
+
+typedef struct ofly_ctx ofly_ctx;       /* one device + one stream; calls on a context are serialised */
+typedef struct ofly_tables ofly_tables; /* immutable, ref-counted EAM tables resident on the device */
+typedef struct ofly_batch ofly_batch;   /* R replicas x N atoms: list-space positions, neighbour lists, workspaces */
+
+/* Message of the last error raised on this host thread. */
+const char *ofly_last_error(void);
+/* Library version string. */
+const char *ofly_version(void);
+
+int ofly_ctx_create(int device, ofly_ctx **out);
+void ofly_ctx_destroy(ofly_ctx *ctx);
+/* The context's cudaStream_t (so a caller can time it with events or order work after it). */
+void *ofly_ctx_stream(ofly_ctx *ctx);
+int ofly_ctx_synchronize(ofly_ctx *ctx);
+/* Number of kernels this context has launched so far. */
+long ofly_ctx_launch_count(ofly_ctx *ctx);
+
+/* ---- EAM tables: potential::DataEAM -------------------------------------------------------- */
+
+/* Parse a LAMMPS setfl eam/fs file and build the natural cubic splines (data.cpp:67-153,
+ * src/utility/spline.cpp:27-103), then upload the knots. */
+int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out);
+void ofly_tables_retain(ofly_tables *t);
+void ofly_tables_release(ofly_tables *t);
+/* info = {n_types, n_knots_F, n_knots_r}; dinfo = {d_rho, d_r, r_cut, mass[0..n_types)} */
+int ofly_tables_info(const ofly_tables *t, long info[3], double *dinfo);
+/* Copy one spline's knots {a,b,c,d} x n_knots to host. kind: 0 = F_i, 1 = phi(i -> j), 2 = V_ij. */
+int ofly_tables_knots(const ofly_tables *t, int kind, int i, int j, double *out_host);
+/* Host-only variants (no device needed): parse + spline a setfl file and return its header / one
+ * spline's knots. Same arithmetic as ofly_tables_load_setfl; used to check tables bit for bit. */
+int ofly_setfl_info_host(const char *path, long info[3], double *dinfo);
+int ofly_setfl_knots_host(const char *path, int kind, int i, int j, double *out_host);
+/* Generic::r_cut() (generic.hpp:79). */
+double ofly_eam_r_cut(const ofly_tables *t);
+
+/* ---- batch ---------------------------------------------------------------------------------- */
+
+/* extents: orthorhombic box lengths (system::Box with skew < 1e-4, box.hpp:63-76); periodic: per axis. */
+int ofly_batch_create(ofly_ctx *ctx, ofly_tables *tables, const double extents[3], const int periodic[3], long n_atoms,
+                      long n_replicas, const uint32_t *type_host, const uint8_t *frozen_host, ofly_batch **out);
+void ofly_batch_destroy(ofly_batch *b);
+long ofly_batch_atoms(const ofly_batch *b);
+long ofly_batch_replicas(const ofly_batch *b);
+
+/* ---- neigh::List ---------------------------------------------------------------------------- */
+
+/* List(box, r_list) + rebuild(positions) (list.cpp:53-95) for every replica. pos: [R][3N]. */
+int ofly_neigh_rebuild(ofly_batch *b, double r_list, const double *pos_host);
+int ofly_neigh_rebuild_dev(ofly_batch *b, double r_list, const double *pos_dev);
+/* update(x): r <- r - x for real atoms and their images (list.cpp:37-51). delta: [R][3N]. */
+int ofly_neigh_update(ofly_batch *b, const double *delta_host);
+int ofly_neigh_update_dev(ofly_batch *b, const double *delta_dev);
+/* Stored (unfiltered) neighbour lists of one replica as (real index, image shift code) pairs,
+ * shift code = (sx+1) + 3(sy+1) + 9(sz+1). counts: [N]; idx/shift: flattened, capacity cap;
+ * *total receives the number of pairs (may exceed cap, then only cap were written). */
+int ofly_neigh_export(ofly_batch *b, long replica, int *counts_host, int *idx_host, int *shift_host, long cap, long *total);
+/* HyperGrid::cell_idx (hypergrid.hpp:75-99) of every real atom's canonical image. out: [N]. */
+int ofly_neigh_cells(ofly_batch *b, long replica, int *cell_host);
+/* List-space (canonical, updated) positions of the real atoms of one replica. out: [3N]. */
+int ofly_neigh_positions(ofly_batch *b, long replica, double *pos_host);
+/* Mean stored neighbours per atom over the whole batch (for the roofline's n-bar). */
+int ofly_neigh_mean_count(ofly_batch *b, double *mean);
+
+/* ---- potential::Generic (EAM) over the batch's current list ---------------------------------- */
+
+/* energy (eam.cpp:33-51): out [R]. */
+int ofly_eam_energy(ofly_batch *b, double *energy_host);
+/* gradient (eam.cpp:53-120): out [R][3N]; frozen atoms get zero. */
+int ofly_eam_gradient(ofly_batch *b, double *grad_host);
+int ofly_eam_gradient_dev(ofly_batch *b, double *grad_dev);
+/* hessian (eam.cpp:122-233) of one replica: dense column-major (3N)^2, lower triangle meaningful,
+ * zero rows/cols for frozen atoms. mass_weight != 0 applies Hessian::mass_weight (hessian.hpp:136-143). */
+int ofly_eam_hessian(ofly_batch *b, long replica, int mass_weight, double *hess_host);
+
+/* ---- minimise::LBFGS and saddle::Dimer, whole batch resident on the device -------------------- */
+
+typedef struct ofly_lbfgs_options { /* minimise::LBFGS::Options, lbfgs.hpp:53-88 */
+  int n;
+  int iter_max;
+  double f2norm;
+  double skin_frac;
+  double proj_tol;
+  double max_trust;
+  double min_trust;
+  double grow_trust;
+  double shrink_trust;
+} ofly_lbfgs_options;
+
+typedef struct ofly_dimer_options { /* saddle::Dimer::Options, dimer.hpp:56-98 */
+  int n;
+  int max_steps;
+  int hist_check_freq;
+  int use_history;
+  double f2norm;
+  double skin_frac;
+  double proj_tol;
+  double max_trust;
+  double min_trust;
+  double grow_trust;
+  double shrink_trust;
+  double convex_max;
+} ofly_dimer_options;
+
+typedef struct ofly_rotor_options { /* saddle::Rotor::Options, rotor.hpp:47-60 */
+  int n;
+  int iter_max_rot;
+  int relax_in_convex;
+  double delta_r;
+  double theta_tol;
+} ofly_rotor_options;
+
+void ofly_lbfgs_options_default(ofly_lbfgs_options *o);
+void ofly_dimer_options_default(ofly_dimer_options *o);
+void ofly_rotor_options_default(ofly_rotor_options *o);
+
+/* Per-replica work counters filled by the search calls: {grad_evals, rebuilds, updates, steps}. */
+#define OFLY_NUM_COUNTERS 4
+
+/* LBFGS::minimise for every replica. pos_in/pos_out/grad_out: [R][3N].
+ * status[r]: 0 converged, 1 iter_max (the reference returns this bool inverted, lbfgs.hpp:108-118),
+ * -5 Spline::OutOfBounds was hit (reference: exception), -6 neighbour capacity fault.
+ * counters: [R][OFLY_NUM_COUNTERS] or NULL. */
+int ofly_lbfgs_minimise(ofly_batch *b, const ofly_lbfgs_options *opt, const double *pos_in_host, double *pos_out_host,
+                        double *grad_out_host, int *status_host, long *counters_host);
+int ofly_lbfgs_minimise_dev(ofly_batch *b, const ofly_lbfgs_options *opt, const double *pos_in_dev, double *pos_out_dev,
+                            double *grad_out_dev, int *status_dev, long *counters_dev);
+
+/* Dimer::find_sp for every replica. pos/axis in and out: [R][3N]; in_min: [3N]; hist_sp: [n_hist][3N].
+ * exit_code[r]: Dimer::Exit (dimer.hpp:123-129: 0 success, -1 convex, -2 iter_max, -3 collision),
+ * -5 Spline::OutOfBounds, -6 neighbour capacity fault. */
+int ofly_dimer_find_sp(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, const double *pos_in_host,
+                       const double *axis_in_host, const double *in_min_host, const double *hist_sp_host, long n_hist,
+                       double theta_tol, int count_frozen, double *pos_out_host, double *axis_out_host, int *exit_code_host,
+                       long *counters_host);
+int ofly_dimer_find_sp_dev(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, const double *pos_in_dev,
+                           const double *axis_in_dev, const double *in_min_dev, const double *hist_sp_dev, long n_hist,
+                           double theta_tol, int count_frozen, double *pos_out_dev, double *axis_out_dev, int *exit_code_dev,
+                           long *counters_dev);
+
+/* Plain device allocation helpers so a host program needs no CUDA headers of its own. */
+int ofly_dev_alloc(ofly_ctx *ctx, size_t bytes, void **out_dev);
+int ofly_dev_free(ofly_ctx *ctx, void *dev);
+int ofly_dev_upload(ofly_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int ofly_dev_download(ofly_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENFLY_B200_H */

@@ -1,0 +1,598 @@
+// C ABI implementation (include/openfly_b200.h): contexts, EAM tables, batches, neigh::List and
+// potential::Generic entry points. The search entry points live in search_api.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "eam.cuh"
+#include "hessian.cuh"
+#include "internal.hpp"
+#include "neigh.cuh"
+
+namespace ofly {
+
+  static thread_local std::string g_last_error;
+  void set_last_error(std::string const &m) { g_last_error = m; }
+
+  template <typename F>
+  static int guarded(F &&f) {
+    try {
+      f();
+      return OFLY_OK;
+    } catch (Error const &e) {
+      set_last_error(e.what());
+      return e.code;
+    } catch (std::bad_alloc const &) {
+      set_last_error("host allocation failed");
+      return OFLY_ERR_INVALID;
+    } catch (std::exception const &e) {
+      set_last_error(e.what());
+      return OFLY_ERR_INVALID;
+    }
+  }
+
+  static void require(bool ok, char const *msg) {
+    if (!ok) throw Error(OFLY_ERR_INVALID, msg);
+  }
+
+  static void use(ofly_ctx *ctx) { OFLY_CUDA(cudaSetDevice(ctx->device)); }
+
+  static int env_int(char const *name, int dflt) {
+    char const *v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+  }
+
+  // Lanes per atom for the sub-warp kernels: few atoms -> wide groups (more threads in flight),
+  // many atoms -> narrow groups (fewer idle lanes on the ragged row tail).
+  int pick_group(ofly_ctx *ctx, long atoms) {
+    int forced = env_int("OFLY_GROUP", 0);
+    if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    long slots = (long)ctx->sm_count * 2048;
+    if (atoms * 4 >= 2 * slots) return 4;
+    if (atoms * 8 >= 2 * slots) return 8;
+    if (atoms * 16 >= slots) return 16;
+    return 32;
+  }
+
+  template <typename K, typename... A>
+  static void launch(ofly_ctx *ctx, K kernel, size_t threads_total, int block, A... args) {
+    if (threads_total == 0) return;
+    unsigned grid = (unsigned)((threads_total + block - 1) / block);
+    kernel<<<grid, block, 0, ctx->stream>>>(args...);
+    ctx->launches++;
+    OFLY_CUDA(cudaGetLastError());
+  }
+
+  // ---- grid set-up: HyperGrid ctor (hypergrid.hpp:43-56) --------------------------------------------
+  static void make_grid(ofly_batch *b, double r_list) {
+    GridDev g{};
+    require(r_list > 0, "r_cut is negative");
+    for (int i = 0; i < 3; i++) {
+      require(b->extents[i] > r_list, "r_cut is too big for the box");
+      g.shape[i] = 2 + (int)(b->extents[i] / r_list);
+      g.cell[i] = b->extents[i] / std::floor(b->extents[i] / r_list);
+      g.inv_cell[i] = 1.0 / g.cell[i];
+    }
+    g.prod[0] = 1, g.prod[1] = g.shape[0], g.prod[2] = g.shape[0] * g.shape[1];
+    g.ncells = g.shape[0] * g.shape[1] * g.shape[2];
+    g.r_list = r_list;
+    g.r_list_sq = r_list * r_list;
+    b->d.grid = g;
+    b->r_list = r_list;
+
+    size_t R = (size_t)b->R;
+    b->cell_count.reserve(R * g.ncells);
+    b->cell_start.reserve(R * (g.ncells + 1));
+    b->d.cell_count = b->cell_count.p, b->d.cell_start = b->cell_start.p;
+
+    // Expected images per atom for a uniform density, with head-room; regrown on overflow.
+    double ratio = 1;
+    for (int i = 0; i < 3; i++) {
+      if (b->periodic[i]) ratio *= 1 + std::min(2.0, 2 * r_list / b->extents[i]);
+    }
+    long cap = std::min<long>(27 * b->N, (long)(1.3 * ratio * (double)b->N) + 64);
+    if (cap > b->d.img_cap) {
+      b->cell_items.reserve(R * cap), b->img_pos.reserve(R * cap);
+      b->d.img_cap = cap;
+    }
+    b->d.cell_items = b->cell_items.p, b->d.img_pos = b->img_pos.p;
+
+    // Expected neighbours per atom, with head-room; regrown on overflow.
+    double vol = b->extents[0] * b->extents[1] * b->extents[2];
+    double expect = (double)b->N / vol * (4.0 / 3.0) * M_PI * r_list * r_list * r_list;
+    int K = (int)(1.4 * expect) + 16;
+    K = (K + 7) / 8 * 8;
+    if (K > b->d.K) {
+      b->nbr.reserve(R * (size_t)b->N * K);
+      b->d.K = K;
+    }
+    b->d.nbr = b->nbr.p;
+  }
+
+  static void grow_after_fault(ofly_batch *b) {
+    size_t R = (size_t)b->R;
+    // Which bound was hit is not recorded separately; grow both (rare path).
+    long cap = std::min<long>(27 * b->N, b->d.img_cap * 2);
+    b->cell_items.release(), b->img_pos.release();
+    b->cell_items.reserve(R * cap), b->img_pos.reserve(R * cap);
+    b->d.img_cap = cap, b->d.cell_items = b->cell_items.p, b->d.img_pos = b->img_pos.p;
+    int K = b->d.K * 2;
+    b->nbr.release();
+    b->nbr.reserve(R * (size_t)b->N * K);
+    b->d.K = K, b->d.nbr = b->nbr.p;
+  }
+
+  void enqueue_rebuild(ofly_batch *b, const double *pos_dev) {
+    ofly_ctx *ctx = b->ctx;
+    size_t atoms = (size_t)b->R * b->N;
+    launch(ctx, k_nb_zero, std::min<size_t>((size_t)b->R * b->d.grid.ncells, 1 << 20), 256, b->d);
+    launch(ctx, k_nb_canon_count, atoms, 256, b->d, pos_dev);
+    k_nb_scan<<<(unsigned)b->R, 1024, 0, ctx->stream>>>(b->d);
+    ctx->launches++;
+    launch(ctx, k_nb_scatter, atoms, 256, b->d);
+    launch(ctx, k_nb_sort_cells, (size_t)b->R * b->d.grid.ncells, 128, b->d);
+    switch (pick_group(ctx, (long)atoms)) {
+      case 32:
+        launch(ctx, k_nb_build<32>, atoms * 32, 256, b->d);
+        break;
+      case 16:
+        launch(ctx, k_nb_build<16>, atoms * 16, 256, b->d);
+        break;
+      default:
+        launch(ctx, k_nb_build<8>, atoms * 8, 256, b->d);
+        break;
+    }
+    OFLY_CUDA(cudaGetLastError());
+  }
+
+  // Synchronise and fold the per-replica fault words; returns the OR of all of them.
+  int collect_faults(ofly_batch *b) {
+    b->fault_host.resize((size_t)b->R);
+    OFLY_CUDA(cudaMemcpyAsync(b->fault_host.data(), b->fault.p, sizeof(int) * (size_t)b->R, cudaMemcpyDeviceToHost, b->ctx->stream));
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    int all = 0;
+    for (int f : b->fault_host) all |= f;
+    return all;
+  }
+  static void clear_faults(ofly_batch *b) { OFLY_CUDA(cudaMemsetAsync(b->fault.p, 0, sizeof(int) * (size_t)b->R, b->ctx->stream)); }
+
+  static void rebuild_checked(ofly_batch *b, double r_list, const double *pos_dev) {
+    use(b->ctx);
+    if (!(b->r_list == r_list)) make_grid(b, r_list);
+    for (int attempt = 0;; attempt++) {
+      enqueue_rebuild(b, pos_dev);
+      int f = collect_faults(b);
+      if (!(f & kFaultCapacity)) break;
+      if (attempt == 3) throw Error(OFLY_ERR_CAPACITY, "neighbour buffers overflowed after regrowing");
+      grow_after_fault(b);
+    }
+    b->built = true;
+  }
+
+  void enqueue_gradient(ofly_batch *b, double *grad_dev) {
+    ofly_ctx *ctx = b->ctx;
+    size_t atoms = (size_t)b->R * b->N;
+    TablesDev const &T = b->tables->dev;
+    switch (pick_group(ctx, (long)atoms)) {
+      case 32:
+        launch(ctx, k_eam_rho<32>, atoms * 32, 256, b->d, T);
+        launch(ctx, k_eam_force<32>, atoms * 32, 256, b->d, T, grad_dev);
+        break;
+      case 16:
+        launch(ctx, k_eam_rho<16>, atoms * 16, 256, b->d, T);
+        launch(ctx, k_eam_force<16>, atoms * 16, 256, b->d, T, grad_dev);
+        break;
+      case 8:
+        launch(ctx, k_eam_rho<8>, atoms * 8, 256, b->d, T);
+        launch(ctx, k_eam_force<8>, atoms * 8, 256, b->d, T, grad_dev);
+        break;
+      default:
+        launch(ctx, k_eam_rho<4>, atoms * 4, 256, b->d, T);
+        launch(ctx, k_eam_force<4>, atoms * 4, 256, b->d, T, grad_dev);
+        break;
+    }
+  }
+
+  // used by search_api.cu
+  void make_grid_for(ofly_batch *b, double r_list) { make_grid(b, r_list); }
+  void grow_buffers(ofly_batch *b) { grow_after_fault(b); }
+
+  static void throw_on_fault(int f) {
+    if (f & kFaultOutOfBounds) throw Error(OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region (Spline::OutOfBounds)");
+    if (f & kFaultCapacity) throw Error(OFLY_ERR_CAPACITY, "neighbour capacity fault");
+  }
+
+  static size_t vec_count(ofly_batch *b) { return (size_t)b->R * 3 * (size_t)b->N; }
+
+}  // namespace ofly
+
+using namespace ofly;
+
+extern "C" {
+
+const char *ofly_last_error(void) { return g_last_error.c_str(); }
+const char *ofly_version(void) { return "openfly_b200 0.1 (sm_100a)"; }
+
+int ofly_ctx_create(int device, ofly_ctx **out) {
+  return guarded([&] {
+    require(out != nullptr, "null output pointer");
+    int count = 0;
+    OFLY_CUDA(cudaGetDeviceCount(&count));
+    require(device >= 0 && device < count, "no such CUDA device");
+    auto *c = new ofly_ctx;
+    c->device = device;
+    OFLY_CUDA(cudaSetDevice(device));
+    OFLY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    OFLY_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    OFLY_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *out = c;
+  });
+}
+void ofly_ctx_destroy(ofly_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+void *ofly_ctx_stream(ofly_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int ofly_ctx_synchronize(ofly_ctx *ctx) {
+  return guarded([&] {
+    use(ctx);
+    OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+long ofly_ctx_launch_count(ofly_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- tables ------------------------------------------------------------------------------------
+int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out) {
+  return guarded([&] {
+    require(ctx && path && out, "null argument");
+    use(ctx);
+    auto *t = new ofly_tables;
+    try {
+      t->ctx = ctx;
+      t->host = read_setfl(path);
+      HostTables const &h = t->host;
+      static_assert(sizeof(Knot) == sizeof(double4), "knot layout");
+      t->F.reserve(h.F.size()), t->phi.reserve(h.phi.size()), t->V.reserve(h.V.size());
+      OFLY_CUDA(cudaMemcpy(t->F.p, h.F.data(), h.F.size() * sizeof(Knot), cudaMemcpyHostToDevice));
+      OFLY_CUDA(cudaMemcpy(t->phi.p, h.phi.data(), h.phi.size() * sizeof(Knot), cudaMemcpyHostToDevice));
+      OFLY_CUDA(cudaMemcpy(t->V.p, h.V.data(), h.V.size() * sizeof(Knot), cudaMemcpyHostToDevice));
+      TablesDev &d = t->dev;
+      d.F = t->F.p, d.phi = t->phi.p, d.V = t->V.p;
+      d.n_types = h.n_types, d.kF = (int)h.knots_rho, d.kR = (int)h.knots_r;
+      d.dF = h.d_rho, d.inv_dF = 1 / h.d_rho, d.dR = h.d_r, d.inv_dR = 1 / h.d_r;  // spline.cpp:27 (m_inv_dx = 1/dx)
+      d.r_cut = h.r_cut, d.r_cut_sq = h.r_cut * h.r_cut;
+    } catch (...) {
+      delete t;
+      throw;
+    }
+    *out = t;
+  });
+}
+void ofly_tables_retain(ofly_tables *t) {
+  if (t) t->refs++;
+}
+void ofly_tables_release(ofly_tables *t) {
+  if (t && --t->refs == 0) {
+    cudaSetDevice(t->ctx->device);
+    t->F.release(), t->phi.release(), t->V.release();
+    delete t;
+  }
+}
+int ofly_tables_info(const ofly_tables *t, long info[3], double *dinfo) {
+  return guarded([&] {
+    require(t && info && dinfo, "null argument");
+    info[0] = t->host.n_types, info[1] = t->host.knots_rho, info[2] = t->host.knots_r;
+    dinfo[0] = t->host.d_rho, dinfo[1] = t->host.d_r, dinfo[2] = t->host.r_cut;
+    for (int i = 0; i < t->host.n_types; i++) dinfo[3 + i] = t->host.mass[(size_t)i];
+  });
+}
+int ofly_tables_knots(const ofly_tables *t, int kind, int i, int j, double *out_host) {
+  return guarded([&] {
+    require(t && out_host, "null argument");
+    int n = t->host.n_types;
+    require(i >= 0 && i < n && j >= 0 && j < n && kind >= 0 && kind <= 2, "bad table selector");
+    cudaSetDevice(t->ctx->device);
+    if (kind == 0) {
+      OFLY_CUDA(cudaMemcpy(out_host, t->F.p + (size_t)i * t->host.knots_rho, sizeof(Knot) * t->host.knots_rho, cudaMemcpyDeviceToHost));
+    } else if (kind == 1) {
+      OFLY_CUDA(cudaMemcpy(out_host, t->phi.p + (size_t)(i + n * j) * t->host.knots_r, sizeof(Knot) * t->host.knots_r, cudaMemcpyDeviceToHost));
+    } else {
+      size_t s = (size_t)(std::max(i, j) + n * std::min(i, j));
+      OFLY_CUDA(cudaMemcpy(out_host, t->V.p + s * t->host.knots_r, sizeof(Knot) * t->host.knots_r, cudaMemcpyDeviceToHost));
+    }
+  });
+}
+int ofly_setfl_info_host(const char *path, long info[3], double *dinfo) {
+  return guarded([&] {
+    require(path && info && dinfo, "null argument");
+    HostTables h = read_setfl(path);
+    info[0] = h.n_types, info[1] = h.knots_rho, info[2] = h.knots_r;
+    dinfo[0] = h.d_rho, dinfo[1] = h.d_r, dinfo[2] = h.r_cut;
+    for (int i = 0; i < h.n_types; i++) dinfo[3 + i] = h.mass[(size_t)i];
+  });
+}
+int ofly_setfl_knots_host(const char *path, int kind, int i, int j, double *out_host) {
+  return guarded([&] {
+    require(path && out_host, "null argument");
+    HostTables h = read_setfl(path);
+    int n = h.n_types;
+    require(i >= 0 && i < n && j >= 0 && j < n && kind >= 0 && kind <= 2, "bad table selector");
+    if (kind == 0) {
+      std::memcpy(out_host, h.F.data() + (size_t)i * h.knots_rho, sizeof(Knot) * h.knots_rho);
+    } else if (kind == 1) {
+      std::memcpy(out_host, h.phi.data() + (size_t)(i + n * j) * h.knots_r, sizeof(Knot) * h.knots_r);
+    } else {
+      std::memcpy(out_host, h.V.data() + (size_t)(std::max(i, j) + n * std::min(i, j)) * h.knots_r, sizeof(Knot) * h.knots_r);
+    }
+  });
+}
+double ofly_eam_r_cut(const ofly_tables *t) { return t ? t->host.r_cut : 0.0; }
+
+// ---- batch -------------------------------------------------------------------------------------
+int ofly_batch_create(ofly_ctx *ctx, ofly_tables *tables, const double extents[3], const int periodic[3], long n_atoms,
+                      long n_replicas, const uint32_t *type_host, const uint8_t *frozen_host, ofly_batch **out) {
+  return guarded([&] {
+    require(ctx && tables && extents && periodic && type_host && frozen_host && out, "null argument");
+    require(n_atoms > 0 && n_atoms < (1l << 24), "atom count must be in [1, 2^24)");
+    require(n_replicas > 0 && n_replicas * n_atoms < (1l << 31), "replicas x atoms must fit in 31 bits");
+    use(ctx);
+    auto *b = new ofly_batch;
+    try {
+      b->ctx = ctx, b->tables = tables;
+      ofly_tables_retain(tables);
+      b->N = n_atoms, b->R = n_replicas;
+      b->type_host.resize((size_t)n_atoms);
+      std::vector<uint8_t> fz((size_t)n_atoms);
+      for (long i = 0; i < n_atoms; i++) {
+        // EAM ctor checks the type map against the table (eam.hpp:50-63); here: ids must index the table.
+        require(type_host[i] < (uint32_t)tables->host.n_types, "TypeID outside the EAM table");
+        b->type_host[(size_t)i] = (uint8_t)type_host[i];
+        fz[(size_t)i] = frozen_host[i] ? 1 : 0;
+      }
+      for (int i = 0; i < 3; i++) {
+        require(extents[i] > 0, "Orthorhombic extents are negative");
+        b->extents[i] = extents[i], b->periodic[i] = periodic[i] ? 1 : 0;
+        b->d.box.L[i] = extents[i], b->d.box.invL[i] = 1.0 / extents[i], b->d.box.periodic[i] = b->periodic[i];
+      }
+      size_t atoms = (size_t)b->R * b->N;
+      b->type.reserve((size_t)n_atoms), b->frozen.reserve((size_t)n_atoms);
+      OFLY_CUDA(cudaMemcpy(b->type.p, b->type_host.data(), (size_t)n_atoms, cudaMemcpyHostToDevice));
+      OFLY_CUDA(cudaMemcpy(b->frozen.p, fz.data(), (size_t)n_atoms, cudaMemcpyHostToDevice));
+      b->pos4.reserve(atoms), b->cnt.reserve(atoms), b->cell_of.reserve(atoms), b->fault.reserve((size_t)b->R);
+      OFLY_CUDA(cudaMemset(b->fault.p, 0, sizeof(int) * (size_t)b->R));
+      OFLY_CUDA(cudaMemset(b->cnt.p, 0, sizeof(int) * atoms));
+      b->d.N = (int)b->N, b->d.R = (int)b->R, b->d.K = 0, b->d.img_cap = 0;
+      b->d.type = b->type.p, b->d.frozen = b->frozen.p, b->d.pos4 = b->pos4.p, b->d.cnt = b->cnt.p, b->d.cell_of = b->cell_of.p;
+      b->d.fault = b->fault.p;
+    } catch (...) {
+      ofly_batch_destroy(b);
+      throw;
+    }
+    *out = b;
+  });
+}
+void ofly_batch_destroy(ofly_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->cell_items.release();
+  b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release();
+  b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();
+  ofly_tables_release(b->tables);
+  delete b;
+}
+long ofly_batch_atoms(const ofly_batch *b) { return b ? b->N : 0; }
+long ofly_batch_replicas(const ofly_batch *b) { return b ? b->R : 0; }
+
+// ---- neigh::List ---------------------------------------------------------------------------------
+int ofly_neigh_rebuild_dev(ofly_batch *b, double r_list, const double *pos_dev) {
+  return guarded([&] {
+    require(b && pos_dev, "null argument");
+    rebuild_checked(b, r_list, pos_dev);
+  });
+}
+int ofly_neigh_rebuild(ofly_batch *b, double r_list, const double *pos_host) {
+  return guarded([&] {
+    require(b && pos_host, "null argument");
+    use(b->ctx);
+    b->stage_a.reserve(vec_count(b));
+    OFLY_CUDA(cudaMemcpyAsync(b->stage_a.p, pos_host, sizeof(double) * vec_count(b), cudaMemcpyHostToDevice, b->ctx->stream));
+    rebuild_checked(b, r_list, b->stage_a.p);
+  });
+}
+int ofly_neigh_update_dev(ofly_batch *b, const double *delta_dev) {
+  return guarded([&] {
+    require(b && delta_dev, "null argument");
+    require(b->built, "update() before rebuild()");
+    use(b->ctx);
+    launch(b->ctx, k_nb_update, (size_t)b->R * b->N, 256, b->d, delta_dev);
+  });
+}
+int ofly_neigh_update(ofly_batch *b, const double *delta_host) {
+  return guarded([&] {
+    require(b && delta_host, "null argument");
+    require(b->built, "update() before rebuild()");
+    use(b->ctx);
+    b->stage_a.reserve(vec_count(b));
+    OFLY_CUDA(cudaMemcpyAsync(b->stage_a.p, delta_host, sizeof(double) * vec_count(b), cudaMemcpyHostToDevice, b->ctx->stream));
+    launch(b->ctx, k_nb_update, (size_t)b->R * b->N, 256, b->d, (const double *)b->stage_a.p);
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  });
+}
+int ofly_neigh_export(ofly_batch *b, long replica, int *counts_host, int *idx_host, int *shift_host, long cap, long *total) {
+  return guarded([&] {
+    require(b && counts_host && idx_host && shift_host && total, "null argument");
+    require(b->built, "export before rebuild()");
+    require(replica >= 0 && replica < b->R, "replica out of range");
+    use(b->ctx);
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    std::vector<int> cnt((size_t)b->N);
+    std::vector<uint32_t> rows((size_t)b->N * b->d.K);
+    OFLY_CUDA(cudaMemcpy(cnt.data(), b->cnt.p + (size_t)replica * b->N, sizeof(int) * (size_t)b->N, cudaMemcpyDeviceToHost));
+    OFLY_CUDA(cudaMemcpy(rows.data(), b->nbr.p + (size_t)replica * b->N * b->d.K, sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost));
+    long w = 0;
+    for (long i = 0; i < b->N; i++) {
+      counts_host[i] = cnt[(size_t)i];
+      for (int k = 0; k < cnt[(size_t)i]; k++, w++) {
+        if (w < cap) {
+          uint32_t e = rows[(size_t)i * b->d.K + k];
+          idx_host[w] = (int)(e & kIdxMask), shift_host[w] = (int)((e >> 24) & 31u);
+        }
+      }
+    }
+    *total = w;
+  });
+}
+int ofly_neigh_cells(ofly_batch *b, long replica, int *cell_host) {
+  return guarded([&] {
+    require(b && cell_host, "null argument");
+    require(b->built, "cells before rebuild()");
+    require(replica >= 0 && replica < b->R, "replica out of range");
+    use(b->ctx);
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    OFLY_CUDA(cudaMemcpy(cell_host, b->cell_of.p + (size_t)replica * b->N, sizeof(int) * (size_t)b->N, cudaMemcpyDeviceToHost));
+  });
+}
+int ofly_neigh_positions(ofly_batch *b, long replica, double *pos_host) {
+  return guarded([&] {
+    require(b && pos_host, "null argument");
+    require(b->built, "positions before rebuild()");
+    require(replica >= 0 && replica < b->R, "replica out of range");
+    use(b->ctx);
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    std::vector<double4> p((size_t)b->N);
+    OFLY_CUDA(cudaMemcpy(p.data(), b->pos4.p + (size_t)replica * b->N, sizeof(double4) * (size_t)b->N, cudaMemcpyDeviceToHost));
+    for (long i = 0; i < b->N; i++) pos_host[3 * i] = p[(size_t)i].x, pos_host[3 * i + 1] = p[(size_t)i].y, pos_host[3 * i + 2] = p[(size_t)i].z;
+  });
+}
+int ofly_neigh_mean_count(ofly_batch *b, double *mean) {
+  return guarded([&] {
+    require(b && mean, "null argument");
+    require(b->built, "mean_count before rebuild()");
+    use(b->ctx);
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    std::vector<int> cnt((size_t)b->R * b->N);
+    OFLY_CUDA(cudaMemcpy(cnt.data(), b->cnt.p, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost));
+    double s = 0;
+    for (int c : cnt) s += c;
+    *mean = s / (double)cnt.size();
+  });
+}
+
+// ---- potential::Generic --------------------------------------------------------------------------
+int ofly_eam_gradient_dev(ofly_batch *b, double *grad_dev) {
+  return guarded([&] {
+    require(b && grad_dev, "null argument");
+    require(b->built, "gradient() before rebuild()");
+    require(b->tables->host.r_cut <= b->r_list, "r_cut is bigger than the internal r_cut");  // list.hpp:141-143
+    use(b->ctx);
+    enqueue_gradient(b, grad_dev);
+  });
+}
+int ofly_eam_gradient(ofly_batch *b, double *grad_host) {
+  return guarded([&] {
+    require(b && grad_host, "null argument");
+    require(b->built, "gradient() before rebuild()");
+    require(b->tables->host.r_cut <= b->r_list, "r_cut is bigger than the internal r_cut");
+    use(b->ctx);
+    b->stage_b.reserve(vec_count(b));
+    clear_faults(b);
+    enqueue_gradient(b, b->stage_b.p);
+    OFLY_CUDA(cudaMemcpyAsync(grad_host, b->stage_b.p, sizeof(double) * vec_count(b), cudaMemcpyDeviceToHost, b->ctx->stream));
+    throw_on_fault(collect_faults(b));
+  });
+}
+int ofly_eam_energy(ofly_batch *b, double *energy_host) {
+  return guarded([&] {
+    require(b && energy_host, "null argument");
+    require(b->built, "energy() before rebuild()");
+    require(b->tables->host.r_cut <= b->r_list, "r_cut is bigger than the internal r_cut");
+    use(b->ctx);
+    size_t atoms = (size_t)b->R * b->N;
+    b->scratch.reserve(atoms + (size_t)b->R);
+    clear_faults(b);
+    TablesDev const &T = b->tables->dev;
+    switch (pick_group(b->ctx, (long)atoms)) {
+      case 32:
+        launch(b->ctx, k_eam_energy_atoms<32>, atoms * 32, 256, b->d, T, b->scratch.p);
+        break;
+      case 16:
+        launch(b->ctx, k_eam_energy_atoms<16>, atoms * 16, 256, b->d, T, b->scratch.p);
+        break;
+      default:
+        launch(b->ctx, k_eam_energy_atoms<8>, atoms * 8, 256, b->d, T, b->scratch.p);
+        break;
+    }
+    k_reduce_rows<<<(unsigned)b->R, 1024, 0, b->ctx->stream>>>(b->scratch.p, (int)b->N, b->scratch.p + atoms);
+    b->ctx->launches++;
+    OFLY_CUDA(cudaMemcpyAsync(energy_host, b->scratch.p + atoms, sizeof(double) * (size_t)b->R, cudaMemcpyDeviceToHost, b->ctx->stream));
+    throw_on_fault(collect_faults(b));
+  });
+}
+int ofly_eam_hessian(ofly_batch *b, long replica, int mass_weight, double *hess_host) {
+  return guarded([&] {
+    require(b && hess_host, "null argument");
+    require(b->built, "hessian() before rebuild()");
+    require(replica >= 0 && replica < b->R, "replica out of range");
+    require(b->tables->host.r_cut <= b->r_list, "r_cut is bigger than the internal r_cut");
+    use(b->ctx);
+    size_t n3 = 3 * (size_t)b->N;
+    DevBuf<double> H, aux, mass;
+    try {
+      H.reserve(n3 * n3), aux.reserve(4 * (size_t)b->N), mass.reserve(kMaxTypes);
+      std::vector<double> m(kMaxTypes, 1.0);
+      for (int t = 0; t < b->tables->host.n_types; t++) m[(size_t)t] = b->tables->host.mass[(size_t)t];
+      OFLY_CUDA(cudaMemcpyAsync(mass.p, m.data(), sizeof(double) * kMaxTypes, cudaMemcpyHostToDevice, b->ctx->stream));
+      OFLY_CUDA(cudaMemsetAsync(H.p, 0, sizeof(double) * n3 * n3, b->ctx->stream));
+      clear_faults(b);
+      launch(b->ctx, k_hess_rho_mu<8>, (size_t)b->N * 8, 256, b->d, b->tables->dev, (int)replica, aux.p);
+      launch(b->ctx, k_hess_columns<32>, (size_t)b->N * 32, 256, b->d, b->tables->dev, (int)replica, (const double *)aux.p, H.p);
+      if (mass_weight) launch(b->ctx, k_hess_mass_weight, n3 * n3, 256, H.p, (int)b->N, (const uint8_t *)b->type.p, (const double *)mass.p);
+      OFLY_CUDA(cudaMemcpyAsync(hess_host, H.p, sizeof(double) * n3 * n3, cudaMemcpyDeviceToHost, b->ctx->stream));
+      throw_on_fault(collect_faults(b));
+    } catch (...) {
+      H.release(), aux.release(), mass.release();
+      throw;
+    }
+    H.release(), aux.release(), mass.release();
+  });
+}
+
+// ---- raw device memory helpers -------------------------------------------------------------------
+int ofly_dev_alloc(ofly_ctx *ctx, size_t bytes, void **out_dev) {
+  return guarded([&] {
+    require(ctx && out_dev, "null argument");
+    use(ctx);
+    OFLY_CUDA(cudaMalloc(out_dev, bytes));
+  });
+}
+int ofly_dev_free(ofly_ctx *ctx, void *dev) {
+  return guarded([&] {
+    require(ctx, "null argument");
+    use(ctx);
+    OFLY_CUDA(cudaFree(dev));
+  });
+}
+int ofly_dev_upload(ofly_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+  return guarded([&] {
+    require(ctx && dst_dev && src_host, "null argument");
+    use(ctx);
+    OFLY_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+int ofly_dev_download(ofly_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+  return guarded([&] {
+    require(ctx && dst_host && src_dev, "null argument");
+    use(ctx);
+    OFLY_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+}  // extern "C"

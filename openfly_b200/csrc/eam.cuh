@@ -1,0 +1,190 @@
+// EAM energy / gradient over a device-resident neighbour list -- the B200 counterpart of
+// potential::EAM (src/potential/EAM/eam.cpp:33-120) iterating with neigh::List::for_neighbours
+// (include/libfly/neigh/list.hpp:138-154) and evaluating Spline::f/fp (spline.hpp:81-154).
+//
+// Two-pass, scatter-free gather. A sub-warp of G lanes owns one atom; lanes stride the atom's
+// neighbour row (coalesced 4 B entry loads), fetch each neighbour's {x,y,z,F'} record with one
+// 256-bit load, the spline knot {a,b,c,d} with one 256-bit read-only load, and the G partial sums
+// are combined with a fixed shuffle tree (deterministic order). No atomics, no stores to other atoms.
+//   pass 1: rho_b = sum_a phi_{a->b}(r);  F'_b = F_b'(rho_b) is stored in pos4[b].w   (eam.cpp:62-73)
+//   pass 2: grad_g = - sum_a [V'(r) + F'_g phi'_{a->g}(r) + F'_a phi'_{g->a}(r)] / r * dr (eam.cpp:90-107)
+// The FP64 pipe is the co-limiter of this path, so r and 1/r come from one rsqrt seed + one
+// correction (fast_rsqrt) instead of an IEEE sqrt and an IEEE division.
+#pragma once
+
+#include "device_common.cuh"
+
+namespace ofly {
+
+  struct PairGeom {
+    double dx, dy, dz;  // r_n - r_i, neighbour image minus centre (list.hpp:148)
+    double r2;
+    double fprime_j;  // pos4[j].w
+    int j, tj;
+  };
+
+  // Decode one neighbour entry and fetch its record.
+  __device__ __forceinline__ PairGeom load_pair(const BatchDev &B, const double4 *__restrict__ pos, const double4 &pi, uint32_t e) {
+    PairGeom g;
+    g.j = (int)(e & kIdxMask);
+    g.tj = (int)(e >> 29);
+    int code = (int)((e >> 24) & 31u);
+    double4 pj = ld256(pos + g.j);
+    double sx = 0, sy = 0, sz = 0;
+    if (code != kShiftCentre) {
+      int dxg = code % 3, dyg = (code / 3) % 3, dzg = code / 9;
+      sx = shift_of(dxg, B.box.L[0]), sy = shift_of(dyg, B.box.L[1]), sz = shift_of(dzg, B.box.L[2]);
+    }
+    g.dx = (pj.x + sx) - pi.x;
+    g.dy = (pj.y + sy) - pi.y;
+    g.dz = (pj.z + sz) - pi.z;
+    g.r2 = fma(g.dz, g.dz, fma(g.dy, g.dy, g.dx * g.dx));
+    g.fprime_j = pj.w;
+    return g;
+  }
+
+  // Spline::fetch (spline.hpp:135-154): interval index and offset. Flags OutOfBounds, clamps the read.
+  __device__ __forceinline__ int knot_index(double x, double inv_dx, double dx, int n_knots, double &x0, bool &oob) {
+    int i = __double2int_rz(x * inv_dx);
+    if (i >= n_knots) {
+      oob = true;
+      i = n_knots - 1;
+    }
+    x0 = fma(-(double)i, dx, x);
+    return i;
+  }
+  __device__ __forceinline__ double spline_f(const double4 &k, double x0) { return fma(x0, fma(x0, fma(x0, k.w, k.z), k.y), k.x); }
+  __device__ __forceinline__ double spline_fp(const double4 &k, double x0) { return fma(x0, fma(x0 * 3.0, k.w, 2.0 * k.z), k.y); }
+  __device__ __forceinline__ double spline_fpp(const double4 &k, double x0) { return fma(6.0 * x0, k.w, 2.0 * k.z); }
+
+  // Pass 1 for atom i by a sub-warp of G lanes: returns rho_i on every lane. If `v_sum` is non-null
+  // also accumulates sum_a V(r) (energy, eam.cpp:41-46).
+  template <int G, bool WITH_V>
+  __device__ __forceinline__ double eam_rho_atom(const BatchDev &B, const TablesDev &T, int r, int i, int lane, double *v_sum, bool &oob) {
+    const double4 *pos = B.pos4 + (size_t)r * B.N;
+    const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
+    const int n = B.cnt[(size_t)r * B.N + i];
+    const int ti = B.type[i];
+    const double4 pi = ld256(pos + i);
+    double rho = 0, vs = 0;
+    for (int k = lane; k < n; k += G) {
+      PairGeom g = load_pair(B, pos, pi, row[k]);
+      if (g.r2 < T.r_cut_sq) {
+        double rr = g.r2 * fast_rsqrt(g.r2);
+        double x0;
+        int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
+        rho += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
+        if (WITH_V) {
+          int hi = max(ti, g.tj), lo = min(ti, g.tj);
+          vs += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+        }
+      }
+    }
+    if (WITH_V) *v_sum = group_sum<G>(vs);
+    return group_sum<G>(rho);
+  }
+
+  // Pass 2 for atom i: gradient on every lane.
+  template <int G>
+  __device__ __forceinline__ void eam_force_atom(const BatchDev &B, const TablesDev &T, int r, int i, int lane, double &gx, double &gy,
+                                                 double &gz, bool &oob) {
+    const double4 *pos = B.pos4 + (size_t)r * B.N;
+    const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
+    const int n = B.cnt[(size_t)r * B.N + i];
+    const int ti = B.type[i];
+    const double4 pi = ld256(pos + i);
+    const double Fi = pi.w;
+    double ax = 0, ay = 0, az = 0;
+    for (int k = lane; k < n; k += G) {
+      PairGeom g = load_pair(B, pos, pi, row[k]);
+      if (g.r2 < T.r_cut_sq) {
+        double rinv = fast_rsqrt(g.r2);
+        double rr = g.r2 * rinv;
+        double x0;
+        int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
+        int hi = max(ti, g.tj), lo = min(ti, g.tj);
+        double mag = spline_fp(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+        double p_ji = spline_fp(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);  // phi(a -> g)
+        double p_ij = p_ji;
+        if (g.tj != ti) p_ij = spline_fp(ld256_nc(T.phi + (size_t)(ti + T.n_types * g.tj) * T.kR + idx), x0);  // phi(g -> a)
+        mag = fma(Fi, p_ji, mag);
+        mag = fma(g.fprime_j, p_ij, mag);
+        double s = mag * rinv;
+        ax = fma(-s, g.dx, ax), ay = fma(-s, g.dy, ay), az = fma(-s, g.dz, az);
+      }
+    }
+    gx = group_sum<G>(ax), gy = group_sum<G>(ay), gz = group_sum<G>(az);
+  }
+
+  // F_i'(rho) / F_i(rho) with the OutOfBounds check of Spline::fetch.
+  __device__ __forceinline__ double embed(const TablesDev &T, int ti, double rho, bool deriv, bool &oob) {
+    double x0;
+    int idx = knot_index(rho, T.inv_dF, T.dF, T.kF, x0, oob);
+    double4 k = ld256_nc(T.F + (size_t)ti * T.kF + idx);
+    return deriv ? spline_fp(k, x0) : spline_f(k, x0);
+  }
+
+  // ---- grid-wide kernels -----------------------------------------------------------------------
+
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_eam_rho(BatchDev B, TablesDev T) {
+    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
+    int lane = threadIdx.x % G;
+    if (g >= (size_t)B.R * B.N) return;  // whole sub-warps leave together
+    int r = (int)(g / B.N), i = (int)(g % B.N);
+    bool oob = false;
+    double rho = eam_rho_atom<G, false>(B, T, r, i, lane, nullptr, oob);
+    if (lane == 0) {
+      double fp = embed(T, B.type[i], rho, true, oob);
+      reinterpret_cast<double *>(B.pos4 + (size_t)r * B.N + i)[3] = fp;
+    }
+    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
+  }
+
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_eam_force(BatchDev B, TablesDev T, double *__restrict__ out) {
+    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
+    int lane = threadIdx.x % G;
+    if (g >= (size_t)B.R * B.N) return;
+    int r = (int)(g / B.N), i = (int)(g % B.N);
+    bool oob = false;
+    double gx = 0, gy = 0, gz = 0;
+    if (!B.frozen[i]) eam_force_atom<G>(B, T, r, i, lane, gx, gy, gz, oob);
+    if (lane == 0) {
+      double *o = out + ((size_t)r * B.N + i) * 3;
+      o[0] = gx, o[1] = gy, o[2] = gz;
+    }
+    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
+  }
+
+  // Per-atom energy e_i = 0.5 sum V + F(rho) into scratch[R][N].
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_eam_energy_atoms(BatchDev B, TablesDev T, double *__restrict__ scratch) {
+    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
+    int lane = threadIdx.x % G;
+    if (g >= (size_t)B.R * B.N) return;
+    int r = (int)(g / B.N), i = (int)(g % B.N);
+    bool oob = false;
+    double vs = 0;
+    double rho = eam_rho_atom<G, true>(B, T, r, i, lane, &vs, oob);
+    if (lane == 0) scratch[g] = fma(0.5, vs, embed(T, B.type[i], rho, false, oob));
+    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
+  }
+
+  // One CTA per replica: fixed-order tree sum of scratch[r][0..N) -> out[r].
+  static __global__ void __launch_bounds__(1024) k_reduce_rows(const double *__restrict__ scratch, int N, double *__restrict__ out) {
+    __shared__ double part[32];
+    const double *row = scratch + (size_t)blockIdx.x * N;
+    double s = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s += row[i];
+    s = group_sum<32>(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+      v = group_sum<32>(v);
+      if (threadIdx.x == 0) out[blockIdx.x] = v;
+    }
+  }
+
+}  // namespace ofly

@@ -1,0 +1,86 @@
+// Host-side objects behind the opaque C handles of include/openfly_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/openfly_b200.h"
+#include "device_common.cuh"
+#include "setfl.hpp"
+
+namespace ofly {
+
+  struct Error : std::runtime_error {
+    int code;
+    Error(int c, std::string const &m) : std::runtime_error(m), code(c) {}
+  };
+
+  void set_last_error(std::string const &m);
+
+#define OFLY_CUDA(expr)                                                                                        \
+  do {                                                                                                         \
+    cudaError_t e_ = (expr);                                                                                   \
+    if (e_ != cudaSuccess) {                                                                                   \
+      throw ::ofly::Error(OFLY_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                  \
+    }                                                                                                          \
+  } while (0)
+
+  // Device buffer that grows but never shrinks.
+  template <typename T>
+  struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void reserve(size_t count) {
+      if (count <= n) return;
+      if (p) cudaFree(p);
+      p = nullptr, n = 0;
+      OFLY_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+      n = count;
+    }
+    void release() {
+      if (p) cudaFree(p);
+      p = nullptr, n = 0;
+    }
+  };
+
+}  // namespace ofly
+
+struct ofly_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long launches = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+};
+
+struct ofly_tables {
+  ofly_ctx *ctx = nullptr;
+  ofly::HostTables host;
+  ofly::DevBuf<double4> F, phi, V;
+  ofly::TablesDev dev{};
+  std::atomic<int> refs{1};
+};
+
+struct ofly_batch {
+  ofly_ctx *ctx = nullptr;
+  ofly_tables *tables = nullptr;
+  long N = 0, R = 0;
+  double extents[3] = {0, 0, 0};
+  int periodic[3] = {1, 1, 1};
+  double r_list = -1;  // radius the current grid was made for (-1: none yet)
+  bool built = false;
+  ofly::BatchDev d{};
+  std::vector<uint8_t> type_host;
+
+  ofly::DevBuf<uint8_t> type, frozen;
+  ofly::DevBuf<double4> pos4, img_pos;
+  ofly::DevBuf<uint32_t> nbr, cell_items;
+  ofly::DevBuf<int> cnt, cell_of, cell_count, cell_start, fault;
+  ofly::DevBuf<double> stage_a, stage_b, stage_c, scratch;  // [R][3N] staging for the host-pointer entry points
+  ofly::DevBuf<char> search_ws;                              // workspace of the persistent search kernels
+  std::vector<int> fault_host;
+};

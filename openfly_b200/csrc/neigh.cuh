@@ -1,0 +1,259 @@
+// Cell-list neighbour build / update on the device -- the B200 counterpart of neigh::List
+// (include/libfly/neigh/list.hpp:71-210, src/neigh/list.cpp:37-165).
+//
+// The reference materialises periodic ghost atoms serially (make_ghosts, list.cpp:100-132), links
+// real + ghost atoms into per-cell linked lists and then scans the <=27 adjacent cells of each real
+// atom. Here the same *set* is produced in parallel:
+//   1. canon_count   canonical image of every atom (orthorhombic.hpp:132-139); every valid image
+//                    (a ghost exists per axis iff x < r_list -> x+L, or x > L-r_list -> x-L,
+//                    orthorhombic.hpp:54-74; axes combine independently, which is what ghosts-of-
+//                    ghosts produce) is binned with HyperGrid::cell_idx into a histogram.
+//   2. scan          exclusive scan of the histogram per replica.
+//   3. scatter       each image is written to a slot of its cell as (j | shift code << 24).
+//   4. sort_cells    the few items of a cell are sorted (slot order from atomics is arbitrary, sorting
+//                    makes the final neighbour order -- and so every later sum -- deterministic) and
+//                    the image positions x_j + s*L are written in cell order, one 32 B record each.
+//   5. build         a sub-warp per atom walks the 3x3 rows of adjacent cells (contiguous slots),
+//                    tests (pos_i - pos_n)^2 < r_list^2 in the reference's operation order with
+//                    round-to-nearest intrinsics (bit-exact neighbour sets), and compacts the hits
+//                    into the atom's row with warp ballots.
+// All functions are written against one replica so that both the grid-wide kernels below and the
+// persistent search kernel (search.cuh) can call them.
+#pragma once
+
+#include "device_common.cuh"
+
+namespace ofly {
+
+  // ---- per-atom image enumeration --------------------------------------------------------------
+  template <typename F>
+  __device__ __forceinline__ void for_each_image(const BatchDev &B, double x, double y, double z, F &&f) {
+    const double r = B.grid.r_list;
+    bool okx[3], oky[3], okz[3];
+    okx[0] = B.box.periodic[0] && x > __dsub_rn(B.box.L[0], r), okx[1] = true, okx[2] = B.box.periodic[0] && x < r;
+    oky[0] = B.box.periodic[1] && y > __dsub_rn(B.box.L[1], r), oky[1] = true, oky[2] = B.box.periodic[1] && y < r;
+    okz[0] = B.box.periodic[2] && z > __dsub_rn(B.box.L[2], r), okz[1] = true, okz[2] = B.box.periodic[2] && z < r;
+#pragma unroll
+    for (int sz = 0; sz < 3; sz++) {
+      if (!okz[sz]) continue;
+      double iz = sz == 1 ? z : (sz == 0 ? __dsub_rn(z, B.box.L[2]) : __dadd_rn(z, B.box.L[2]));
+#pragma unroll
+      for (int sy = 0; sy < 3; sy++) {
+        if (!oky[sy]) continue;
+        double iy = sy == 1 ? y : (sy == 0 ? __dsub_rn(y, B.box.L[1]) : __dadd_rn(y, B.box.L[1]));
+#pragma unroll
+        for (int sx = 0; sx < 3; sx++) {
+          if (!okx[sx]) continue;
+          double ix = sx == 1 ? x : (sx == 0 ? __dsub_rn(x, B.box.L[0]) : __dadd_rn(x, B.box.L[0]));
+          f(sx + 3 * sy + 9 * sz, ix, iy, iz);
+        }
+      }
+    }
+  }
+
+  // Step 1 for atom i of replica r. `user_pos` is the caller's [3N] array of this replica.
+  __device__ __forceinline__ void nb_canon_count(const BatchDev &B, const double *__restrict__ user_pos, int r, int i) {
+    double x = user_pos[3 * i], y = user_pos[3 * i + 1], z = user_pos[3 * i + 2];
+    // x - L * floor(x * (1/L))  (orthorhombic.hpp:138)
+    x = __dsub_rn(x, __dmul_rn(B.box.L[0], floor(__dmul_rn(x, B.box.invL[0]))));
+    y = __dsub_rn(y, __dmul_rn(B.box.L[1], floor(__dmul_rn(y, B.box.invL[1]))));
+    z = __dsub_rn(z, __dmul_rn(B.box.L[2], floor(__dmul_rn(z, B.box.invL[2]))));
+    double4 *p = B.pos4 + (size_t)r * B.N + i;
+    st256(p, make_double4(x, y, z, 0.0));
+    int *hist = B.cell_count + (size_t)r * B.grid.ncells;
+    B.cell_of[(size_t)r * B.N + i] = cell_index(B.grid, x, y, z);
+    for_each_image(B, x, y, z, [&](int, double ix, double iy, double iz) { atomicAdd(hist + cell_index(B.grid, ix, iy, iz), 1); });
+  }
+
+  // Step 3 for atom i: the histogram is consumed as a fill cursor (counts go back to zero).
+  __device__ __forceinline__ void nb_scatter(const BatchDev &B, int r, int i) {
+    double4 p = ld256(B.pos4 + (size_t)r * B.N + i);
+    int *hist = B.cell_count + (size_t)r * B.grid.ncells;
+    const int *start = B.cell_start + (size_t)r * (B.grid.ncells + 1);
+    uint32_t *items = B.cell_items + (size_t)r * B.img_cap;
+    for_each_image(B, p.x, p.y, p.z, [&](int code, double ix, double iy, double iz) {
+      int c = cell_index(B.grid, ix, iy, iz);
+      long slot = start[c] + (atomicSub(hist + c, 1) - 1);
+      if (slot < B.img_cap) items[slot] = (uint32_t)i | ((uint32_t)code << 24);
+    });
+  }
+
+  // Step 4 for cell c: insertion sort of its items, then image positions in slot order.
+  __device__ __forceinline__ void nb_sort_cell(const BatchDev &B, int r, int c) {
+    const int *start = B.cell_start + (size_t)r * (B.grid.ncells + 1);
+    long s = start[c], e = start[c + 1];
+    if (e > B.img_cap) e = B.img_cap;
+    uint32_t *items = B.cell_items + (size_t)r * B.img_cap;
+    for (long a = s + 1; a < e; a++) {
+      uint32_t v = items[a];
+      long b = a - 1;
+      while (b >= s && items[b] > v) {
+        items[b + 1] = items[b];
+        b--;
+      }
+      items[b + 1] = v;
+    }
+    double4 *img = B.img_pos + (size_t)r * B.img_cap;
+    const double4 *pos = B.pos4 + (size_t)r * B.N;
+    for (long a = s; a < e; a++) {
+      uint32_t v = items[a];
+      int code = (int)(v >> 24);
+      double4 p = ld256(pos + (v & kIdxMask));
+      int sx = code % 3, sy = (code / 3) % 3, sz = code / 9;
+      double ix = sx == 1 ? p.x : (sx == 0 ? __dsub_rn(p.x, B.box.L[0]) : __dadd_rn(p.x, B.box.L[0]));
+      double iy = sy == 1 ? p.y : (sy == 0 ? __dsub_rn(p.y, B.box.L[1]) : __dadd_rn(p.y, B.box.L[1]));
+      double iz = sz == 1 ? p.z : (sz == 0 ? __dsub_rn(p.z, B.box.L[2]) : __dadd_rn(p.z, B.box.L[2]));
+      st256(img + a, make_double4(ix, iy, iz, __longlong_as_double((long long)v)));
+    }
+  }
+
+  // Step 5 for atom i, executed by the G lanes of one sub-warp (all G lanes must call).
+  template <int G>
+  __device__ __forceinline__ void nb_build_atom(const BatchDev &B, int r, int i, int lane) {
+    const int sub = ((threadIdx.x & 31) / G) * G;  // first lane of this sub-warp inside the warp
+    const unsigned gmask = group_mask<G>();
+
+    double4 pi = ld256(B.pos4 + (size_t)r * B.N + i);
+    const int *start = B.cell_start + (size_t)r * (B.grid.ncells + 1);
+    const double4 *img = B.img_pos + (size_t)r * B.img_cap;
+    uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
+    const uint32_t self = (uint32_t)i | ((uint32_t)kShiftCentre << 24);
+    const double rl2 = B.grid.r_list_sq;
+
+    int c = B.cell_of[(size_t)r * B.N + i];
+    int cx = c % B.grid.shape[0], cy = (c / B.grid.shape[0]) % B.grid.shape[1], cz = c / (B.grid.shape[0] * B.grid.shape[1]);
+    int x0 = max(cx - 1, 0), x1 = min(cx + 1, B.grid.shape[0] - 1);
+
+    int count = 0;
+    for (int oz = max(cz - 1, 0); oz <= min(cz + 1, B.grid.shape[2] - 1); oz++) {
+      for (int oy = max(cy - 1, 0); oy <= min(cy + 1, B.grid.shape[1] - 1); oy++) {
+        int base = oy * B.grid.prod[1] + oz * B.grid.prod[2];
+        long s = start[base + x0], e = start[base + x1 + 1];
+        if (e > B.img_cap) e = B.img_cap;
+        for (long a0 = s; a0 < e; a0 += G) {
+          long a = a0 + lane;
+          bool hit = false;
+          uint32_t entry = 0;
+          if (a < e) {
+            double4 q = ld256(img + a);
+            entry = (uint32_t)__double_as_longlong(q.w);
+            double dx = __dsub_rn(pi.x, q.x), dy = __dsub_rn(pi.y, q.y), dz = __dsub_rn(pi.z, q.z);
+            hit = entry != self && norm_sq_rn(dx, dy, dz) < rl2;
+          }
+          unsigned b = __ballot_sync(gmask, hit) >> sub;  // sub-warps loop independently: ballot over own lanes only
+          if (hit) {
+            int k = count + __popc(b & ((1u << lane) - 1u));
+            if (k < B.K) row[k] = entry | ((uint32_t)B.type[entry & kIdxMask] << 29);
+          }
+          count += __popc(b);
+        }
+      }
+    }
+    if (lane == 0) {
+      B.cnt[(size_t)r * B.N + i] = min(count, B.K);
+      if (count > B.K) atomicOr(B.fault + r, kFaultCapacity);
+    }
+  }
+
+  // update(delta): r <- r - delta (list.cpp:37-51). Images follow implicitly (pos4[j] + s*L).
+  __device__ __forceinline__ void nb_update_atom(const BatchDev &B, const double *__restrict__ delta, int r, int i) {
+    double4 *p = B.pos4 + (size_t)r * B.N + i;
+    double4 v = ld256(p);
+    v.x -= delta[3 * i], v.y -= delta[3 * i + 1], v.z -= delta[3 * i + 2];
+    st256(p, v);
+  }
+
+  // ---- grid-wide kernels (stand-alone List::rebuild / List::update calls) -----------------------
+
+  static __global__ void k_nb_zero(BatchDev B) {
+    size_t n = (size_t)B.R * B.grid.ncells;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) B.cell_count[t] = 0;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < (size_t)B.R; t += (size_t)gridDim.x * blockDim.x) B.fault[t] = 0;
+  }
+
+  static __global__ void k_nb_canon_count(BatchDev B, const double *__restrict__ pos) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)B.R * B.N) return;
+    int r = (int)(t / B.N), i = (int)(t % B.N);
+    nb_canon_count(B, pos + (size_t)r * 3 * B.N, r, i);
+  }
+
+  // Step 2 by one CTA: exclusive scan of the replica's histogram into cell_start[0..ncells].
+  // `sm` is 33 ints of shared memory; every thread of the CTA must call.
+  __device__ __forceinline__ void nb_scan_block(const BatchDev &B, int r, int *sm) {
+    const int *hist = B.cell_count + (size_t)r * B.grid.ncells;
+    int *start = B.cell_start + (size_t)r * (B.grid.ncells + 1);
+    int n = B.grid.ncells;
+    int per = (n + blockDim.x - 1) / blockDim.x;
+    int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int c = lo; c < hi; c++) sum += hist[c];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) sm[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int v = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0;
+      int vi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, vi, o);
+        if (lane >= o) vi += u;
+      }
+      sm[lane] = vi - v;
+      if (lane == 31) sm[32] = vi;
+    }
+    __syncthreads();
+    int run = sm[w] + inc - sum;
+    for (int c = lo; c < hi; c++) {
+      start[c] = run;
+      run += hist[c];
+    }
+    if (threadIdx.x == 0) {
+      start[n] = sm[32];
+      if (sm[32] > B.img_cap) atomicOr(B.fault + r, kFaultCapacity);
+    }
+    __syncthreads();
+  }
+
+  static __global__ void __launch_bounds__(1024) k_nb_scan(BatchDev B) {
+    __shared__ int sm[33];
+    nb_scan_block(B, blockIdx.x, sm);
+  }
+
+  static __global__ void k_nb_scatter(BatchDev B) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)B.R * B.N) return;
+    nb_scatter(B, (int)(t / B.N), (int)(t % B.N));
+  }
+
+  static __global__ void k_nb_sort_cells(BatchDev B) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)B.R * B.grid.ncells) return;
+    nb_sort_cell(B, (int)(t / B.grid.ncells), (int)(t % B.grid.ncells));
+  }
+
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_nb_build(BatchDev B) {
+    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
+    int lane = threadIdx.x % G;
+    // whole sub-warps are in or out together (grid is sized in units of G)
+    if (g >= (size_t)B.R * B.N) {
+      g = (size_t)B.R * B.N - 1;  // tail sub-warps redo the last atom (identical writes) instead of exiting
+    }
+    nb_build_atom<G>(B, (int)(g / B.N), (int)(g % B.N), lane);
+  }
+
+  static __global__ void k_nb_update(BatchDev B, const double *__restrict__ delta) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)B.R * B.N) return;
+    int r = (int)(t / B.N), i = (int)(t % B.N);
+    nb_update_atom(B, delta + (size_t)r * 3 * B.N, r, i);
+  }
+
+}  // namespace ofly

@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's class surface for the force-evaluation path, on top of the C ABI.
+
+Names, argument meaning and error behaviour follow the reference (paths relative to the openFLY tree):
+
+    Box              system::Box                include/libfly/system/box.hpp:84-197 (orthorhombic only)
+    DataEAM          potential::DataEAM         include/libfly/potential/EAM/data.hpp:59-116
+    Generic          potential::Generic (EAM)   include/libfly/potential/generic.hpp:79-136
+    List             neigh::List                include/libfly/neigh/list.hpp:86-161
+    LBFGS            minimise::LBFGS            include/libfly/minimise/LBFGS/lbfgs.hpp:96-118
+    Dimer            saddle::Dimer              include/libfly/saddle/dimer.hpp:107-155
+
+The one deliberate extension: every object works on a *batch* of R replicas of the same system
+([R, N, 3] arrays); R = 1 with [N, 3] arrays is the reference's single-system call. The C++20 shim with
+the same names for a compiled host is include/openfly_b200/fly.hpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import DimerOptions, LbfgsOptions, OflyError, OutOfBounds, RotorOptions, check, f64, ptr  # noqa: F401
+
+_dp, _ip, _lp, _u32p, _u8p = capi._dp, capi._ip, capi._lp, capi._u32p, capi._u8p
+
+
+class Context:
+    """One device + stream (there is no global state; one Context per host thread and device)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        check(self.lib.ofly_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def stream(self) -> int:
+        return int(self.lib.ofly_ctx_stream(self.h) or 0)
+
+    def synchronize(self) -> None:
+        check(self.lib.ofly_ctx_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.ofly_ctx_launch_count(self.h))
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.ofly_ctx_destroy(self.h)
+            self.h = None
+
+    # raw device buffers (bench.py keeps its inputs resident with these)
+    def alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.ofly_dev_alloc(self.h, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def free(self, dev: int) -> None:
+        check(self.lib.ofly_dev_free(self.h, C.c_void_p(dev)))
+
+    def upload(self, dev: int, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a)
+        check(self.lib.ofly_dev_upload(self.h, C.c_void_p(dev), a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def download(self, a: np.ndarray, dev: int) -> None:
+        assert a.flags["C_CONTIGUOUS"]
+        check(self.lib.ofly_dev_download(self.h, a.ctypes.data_as(C.c_void_p), C.c_void_p(dev), a.nbytes))
+
+
+@dataclass
+class Box:
+    """Orthorhombic system::Box: extents (diagonal of the basis) and per-axis periodicity."""
+
+    extents: tuple
+    periodic: tuple = (True, True, True)
+
+    @staticmethod
+    def from_basis(basis, periodic=(True, True, True)) -> "Box":
+        b = np.asarray(basis, dtype=np.float64)
+        skew = b - np.diag(np.diag(b))
+        if np.sqrt((skew * skew).sum()) >= 1e-4:  # box.hpp:63-76 would build a Triclinic cell
+            raise OflyError(capi.OFLY_ERR_INVALID, "triclinic boxes are outside the B200 path (orthorhombic only)")
+        return Box(tuple(np.diag(b)), tuple(bool(p) for p in periodic))
+
+
+class DataEAM:
+    """Parsed + splined setfl tables resident on the device (shared, immutable, ref-counted)."""
+
+    def __init__(self, ctx: Context, path: str):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(ctx.lib.ofly_tables_load_setfl(ctx.h, path.encode(), C.byref(h)))
+        self.h = h
+        info = np.zeros(3, dtype=np.int64)
+        dinfo = np.zeros(3 + 8, dtype=np.float64)
+        check(ctx.lib.ofly_tables_info(self.h, ptr(info, _lp), ptr(dinfo, _dp)))
+        self.n_types, self.knots_rho, self.knots_r = (int(x) for x in info)
+        self.d_rho, self.d_r, self._rcut = (float(x) for x in dinfo[:3])
+        self.mass = dinfo[3:3 + self.n_types].copy()
+
+    def rcut(self) -> float:
+        return self._rcut
+
+    def knots(self, kind: int, i: int, j: int = 0) -> np.ndarray:
+        n = self.knots_rho if kind == 0 else self.knots_r
+        out = np.zeros((n, 4), dtype=np.float64)
+        check(self.ctx.lib.ofly_tables_knots(self.h, kind, i, j, ptr(out, _dp)))
+        return out
+
+    def close(self) -> None:
+        if self.h:
+            self.ctx.lib.ofly_tables_release(self.h)
+            self.h = None
+
+
+class System:
+    """R replicas of one N-atom system: the device-side state shared by List / Generic / LBFGS / Dimer."""
+
+    def __init__(self, data: DataEAM, box: Box, type_id, frozen=None, replicas: int = 1):
+        self.ctx, self.data, self.box = data.ctx, data, box
+        ids = np.ascontiguousarray(type_id, dtype=np.uint32)
+        fz = np.zeros(len(ids), dtype=np.uint8) if frozen is None else np.ascontiguousarray(frozen, dtype=np.uint8)
+        ex = f64(box.extents)
+        pd = np.asarray([1 if p else 0 for p in box.periodic], dtype=np.int32)
+        h = C.c_void_p()
+        check(self.ctx.lib.ofly_batch_create(self.ctx.h, data.h, ptr(ex, _dp), ptr(pd, _ip), len(ids), replicas, ptr(ids, _u32p),
+                                             ptr(fz, _u8p), C.byref(h)))
+        self.h = h
+        self.N, self.R = len(ids), replicas
+        self.type_id, self.frozen = ids, fz
+
+    def _vec(self, a) -> np.ndarray:
+        a = f64(a)
+        if a.size != self.R * self.N * 3:
+            raise OflyError(capi.OFLY_ERR_INVALID, f"expected {self.R}x{self.N}x3 values, got {a.size}")
+        return a.reshape(self.R, self.N, 3)
+
+    def close(self) -> None:
+        if self.h:
+            self.ctx.lib.ofly_batch_destroy(self.h)
+            self.h = None
+
+
+class List:
+    """neigh::List(box, r_cut): rebuild / update / for_neighbours over a System's replicas."""
+
+    def __init__(self, system: System, r_cut: float):
+        self.sys, self.r_cut = system, float(r_cut)
+
+    def size(self) -> int:
+        return self.sys.N
+
+    def rebuild(self, positions, num_threads: int = 1) -> None:
+        if num_threads <= 0:
+            raise OflyError(capi.OFLY_ERR_INVALID, f"{num_threads} is not a valid number of threads for rebuild()")
+        p = self.sys._vec(positions)
+        check(self.sys.ctx.lib.ofly_neigh_rebuild(self.sys.h, self.r_cut, ptr(p, _dp)))
+
+    def update(self, delta) -> None:
+        d = self.sys._vec(delta)
+        check(self.sys.ctx.lib.ofly_neigh_update(self.sys.h, ptr(d, _dp)))
+
+    def export(self, replica: int = 0):
+        """(counts[N], real index[total], shift code[total]) of the stored lists."""
+        s = self.sys
+        counts = np.zeros(s.N, dtype=np.int32)
+        cap = s.N * 512
+        idx = np.zeros(cap, dtype=np.int32)
+        sh = np.zeros(cap, dtype=np.int32)
+        tot = C.c_long()
+        check(s.ctx.lib.ofly_neigh_export(s.h, replica, ptr(counts, _ip), ptr(idx, _ip), ptr(sh, _ip), cap, C.byref(tot)))
+        assert tot.value <= cap
+        return counts, idx[:tot.value].copy(), sh[:tot.value].copy()
+
+    def cells(self, replica: int = 0) -> np.ndarray:
+        out = np.zeros(self.sys.N, dtype=np.int32)
+        check(self.sys.ctx.lib.ofly_neigh_cells(self.sys.h, replica, ptr(out, _ip)))
+        return out
+
+    def positions(self, replica: int = 0) -> np.ndarray:
+        out = np.zeros((self.sys.N, 3), dtype=np.float64)
+        check(self.sys.ctx.lib.ofly_neigh_positions(self.sys.h, replica, ptr(out, _dp)))
+        return out
+
+    def mean_count(self) -> float:
+        m = C.c_double()
+        check(self.sys.ctx.lib.ofly_neigh_mean_count(self.sys.h, C.byref(m)))
+        return m.value
+
+    def for_neighbours(self, i: int, r_cut: float, f, replica: int = 0) -> None:
+        """Call f(n, r, dr) for every neighbour of atom i within r_cut (list.hpp:138-154)."""
+        if r_cut > self.r_cut:
+            raise OflyError(capi.OFLY_ERR_INVALID, f"r_cut={r_cut} is bigger then than the internal r_cut={self.r_cut}")
+        counts, idx, sh = self.export(replica)
+        pos = self.positions(replica)
+        L = np.asarray(self.sys.box.extents)
+        off = int(counts[:i].sum())
+        for k in range(off, off + int(counts[i])):
+            code = int(sh[k])
+            s = np.array([code % 3 - 1, (code // 3) % 3 - 1, code // 9 - 1], dtype=np.float64)
+            dr = (pos[idx[k]] + s * L) - pos[i]
+            r_sq = (dr[0] * dr[0] + dr[1] * dr[1]) + dr[2] * dr[2]
+            if r_sq < r_cut * r_cut:
+                f(int(idx[k]), float(np.sqrt(r_sq)), dr)
+
+
+class Generic:
+    """potential::Generic holding an EAM: r_cut / energy / gradient / hessian over a List."""
+
+    def __init__(self, data: DataEAM):
+        self.data = data
+
+    def r_cut(self) -> float:
+        return self.data.rcut()
+
+    def energy(self, nl: List, num_threads: int = 1) -> np.ndarray:
+        out = np.zeros(nl.sys.R, dtype=np.float64)
+        check(nl.sys.ctx.lib.ofly_eam_energy(nl.sys.h, ptr(out, _dp)))
+        return out
+
+    def gradient(self, nl: List, num_threads: int = 1) -> np.ndarray:
+        out = np.zeros((nl.sys.R, nl.sys.N, 3), dtype=np.float64)
+        check(nl.sys.ctx.lib.ofly_eam_gradient(nl.sys.h, ptr(out, _dp)))
+        return out
+
+    def hessian(self, nl: List, replica: int = 0, mass_weight: bool = False, num_threads: int = 1) -> np.ndarray:
+        """Dense (3N, 3N) array; only the lower triangle is meaningful (system::Hessian)."""
+        n3 = 3 * nl.sys.N
+        out = np.zeros((n3, n3), dtype=np.float64)
+        check(nl.sys.ctx.lib.ofly_eam_hessian(nl.sys.h, replica, 1 if mass_weight else 0, ptr(out, _dp)))
+        return out.T.copy()  # the library writes column-major
+
+
+def lbfgs_options(**kw) -> LbfgsOptions:
+    o = LbfgsOptions()
+    capi.load().ofly_lbfgs_options_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def dimer_options(**kw) -> DimerOptions:
+    o = DimerOptions()
+    capi.load().ofly_dimer_options_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def rotor_options(**kw) -> RotorOptions:
+    o = RotorOptions()
+    capi.load().ofly_rotor_options_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class LBFGS:
+    """minimise::LBFGS(opt, box). minimise() returns (positions, gradient, failed[R], counters[R,4]);
+    failed follows the reference's bool: False on convergence, True on iter_max. A replica that hit
+    Spline::OutOfBounds raises OutOfBounds (the reference throws) unless raise_oob=False, in which case
+    its status is left at -5 in `self.status`."""
+
+    def __init__(self, opt: LbfgsOptions | None = None):
+        self.opt = opt or lbfgs_options()
+        self.status = None
+
+    def minimise(self, system: System, positions, pot: Generic, num_threads: int = 1, raise_oob: bool = True):
+        p = system._vec(positions)
+        out_r = np.zeros_like(p)
+        out_g = np.zeros_like(p)
+        status = np.zeros(system.R, dtype=np.int32)
+        cnt = np.zeros((system.R, 4), dtype=np.int64)
+        check(system.ctx.lib.ofly_lbfgs_minimise(system.h, C.byref(self.opt), ptr(p, _dp), ptr(out_r, _dp), ptr(out_g, _dp),
+                                                 ptr(status, _ip), ptr(cnt, _lp)))
+        self.status = status
+        if raise_oob and (status == -5).any():
+            raise OutOfBounds(capi.OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region")
+        return out_r, out_g, status != 0, cnt
+
+
+class Dimer:
+    """saddle::Dimer(opt, rotor opt, box). find_sp() returns (positions, axis, exit[R], counters[R,4]) with
+    exit codes Dimer::Exit (0 success, -1 convex, -2 iter_max, -3 collision); -5 marks OutOfBounds."""
+
+    success, convex, iter_max, collision, uninit = 0, -1, -2, -3, -4
+
+    def __init__(self, opt: DimerOptions | None = None, r_opt: RotorOptions | None = None):
+        self.opt = opt or dimer_options()
+        self.r_opt = r_opt or rotor_options()
+
+    def find_sp(self, system: System, positions, axis, in_min, pot: Generic, hist_sp=None, theta_tol: float = np.pi / 6,
+                count_frozen: int = 0, num_threads: int = 1, raise_oob: bool = False):
+        p = system._vec(positions)
+        ax = system._vec(axis)
+        mn = f64(in_min).reshape(system.N, 3)
+        hist = f64(np.zeros((0, system.N, 3)) if hist_sp is None else hist_sp).reshape(-1, system.N, 3)
+        out_r = np.zeros_like(p)
+        out_ax = np.zeros_like(p)
+        code = np.zeros(system.R, dtype=np.int32)
+        cnt = np.zeros((system.R, 4), dtype=np.int64)
+        check(system.ctx.lib.ofly_dimer_find_sp(system.h, C.byref(self.opt), C.byref(self.r_opt), ptr(p, _dp), ptr(ax, _dp),
+                                                ptr(mn, _dp), ptr(hist, _dp), hist.shape[0], theta_tol, count_frozen,
+                                                ptr(out_r, _dp), ptr(out_ax, _dp), ptr(code, _ip), ptr(cnt, _lp)))
+        if raise_oob and (code == -5).any():
+            raise OutOfBounds(capi.OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region")
+        return out_r, out_ax, code, cnt

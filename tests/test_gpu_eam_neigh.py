@@ -1,0 +1,175 @@
+"""GPU parity: neigh::List and potential::EAM through the C ABI vs the CPU oracle and the reference goldens."""
+import numpy as np
+import pytest
+
+from tests.common import WEN, bcc_vacancy, golden_cell, pair_multiset
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from openfly_b200 import fly
+
+    ctx = fly.Context(0)
+    data = fly.DataEAM(ctx, WEN)
+    yield fly, ctx, data
+    data.close()
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def otab(oracle_lib):
+    return oracle_lib.Tables(WEN)
+
+
+def test_tables_bit_exact(gpu, otab, oracle_lib):
+    fly, ctx, data = gpu
+    O = oracle_lib
+    assert (data.n_types, data.knots_rho, data.knots_r) == (2, 10004, 10004)
+    assert data.rcut() == otab.rcut
+    for kind, i, j in [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1), (2, 0, 0), (2, 1, 0), (2, 0, 1), (2, 1, 1)]:
+        assert np.array_equal(data.knots(kind, i, j), otab.knots(kind, i, j)), (kind, i, j)
+
+
+def _compare_lists(fly, nl, osys, r_list, pos, replica=0):
+    osys.rebuild(r_list, pos)
+    c0, i0, s0 = osys.export()
+    c1, i1, s1 = nl.export(replica)
+    assert np.array_equal(c0, c1)
+    assert pair_multiset(c0, i0, s0) == pair_multiset(c1, i1, s1)  # bit-exact neighbour sets
+    assert np.array_equal(osys.cells(), nl.cells(replica))          # bit-exact cell ids
+
+
+def test_golden_energy_gradient_hessian(gpu, otab, oracle_lib):
+    """Known answers of tests/potential/EAM/eam.cpp:99-146."""
+    fly, ctx, data = gpu
+    pos, ex, ids = golden_cell()
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(pos)
+    pot = fly.Generic(data)
+    E = pot.energy(nl)[0]
+    assert abs(E - (-2748.5339306065985)) <= 1e-10 * abs(E)
+    g = pot.gradient(nl)[0]
+    assert np.linalg.norm(g[0] - (-0.19182439085483005)) < 1e-10
+    H = pot.hessian(nl)
+    ngd = np.array([[+9.0654715551510830, -1.0875103661087880, -1.0875103661087877],
+                    [-1.0875103661087880, +9.0654715551510830, -1.0875103661087873],
+                    [-1.0875103661087877, -1.0875103661087873, +9.0654715551510830]])
+    assert np.abs(np.tril(H[:3, :3] - ngd)).max() < 1e-10
+    # whole Hessian against the oracle (lower triangle)
+    osys = oracle_lib.System(otab, ex)
+    osys.rebuild(otab.rcut, pos)
+    Ho = osys.hessian(ids, np.zeros(len(ids), np.uint8), threads=8)
+    assert np.abs(np.tril(H) - np.tril(Ho)).max() < 1e-9
+    _compare_lists(fly, nl, osys, otab.rcut, pos)
+    s.close()
+
+
+def test_perfect_cell_zero_modes(gpu):
+    """tests/potential/EAM/eam.cpp:149-188: |g| < 1e-7 and exactly 3 zero Hessian modes."""
+    fly, ctx, data = gpu
+    pos, ex, ids = golden_cell(erase=False)
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(pos)
+    pot = fly.Generic(data)
+    assert np.linalg.norm(pot.gradient(nl)[0]) < 1e-7
+    H = pot.hessian(nl)
+    ev = np.linalg.eigvalsh(np.tril(H) + np.tril(H, -1).T)
+    assert np.all(np.abs(ev[:3]) < 1e-8) and np.all(np.abs(ev[3:]) > 1e-4)
+    s.close()
+
+
+@pytest.mark.parametrize("n,hyd,r_extra", [(10, False, 0.0), (6, True, 0.1731), (4, True, 0.0)])
+def test_parity_vs_oracle(gpu, otab, oracle_lib, n, hyd, r_extra):
+    """C1-style (2000-atom) and C3-style (small box, many ghosts, Fe + H) cells: sets, cells, E, g, update."""
+    fly, ctx, data = gpu
+    pos, ex, ids = bcc_vacancy(n, remove=(1,), jitter=0.05, hydrogen=hyd)
+    fz = np.zeros(len(ids), np.uint8)
+    fz[5] = 1  # one frozen atom: zero gradient but still a density source
+    r_list = data.rcut() + r_extra
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz)
+    nl = fly.List(s, r_list)
+    nl.rebuild(pos)
+    osys = oracle_lib.System(otab, ex)
+    _compare_lists(fly, nl, osys, r_list, pos)
+    pot = fly.Generic(data)
+    E, Eo = pot.energy(nl)[0], osys.energy(ids, 4)
+    assert abs(E - Eo) <= 1e-10 * abs(Eo)
+    g, go = pot.gradient(nl)[0], osys.gradient(ids, fz, 4)
+    assert np.abs(g - go).max() < 1e-9
+    assert np.all(g[5] == 0)
+    # update(): r <- r - delta on both sides, same lists
+    rng = np.random.default_rng(7)
+    delta = rng.normal(0, 0.01, pos.shape)
+    nl.update(delta)
+    osys.update(delta)
+    g, go = pot.gradient(nl)[0], osys.gradient(ids, fz, 4)
+    assert np.abs(g - go).max() < 1e-9
+    E, Eo = pot.energy(nl)[0], osys.energy(ids, 4)
+    assert abs(E - Eo) <= 1e-10 * abs(Eo)
+    s.close()
+
+
+def test_batched_replicas_independent(gpu, otab, oracle_lib):
+    fly, ctx, data = gpu
+    base, ex, ids = bcc_vacancy(6, a=2.855, remove=(1,), hydrogen=True)
+    R = 5
+    pos = np.stack([oracle_lib.jitter(base, (1, 2, 3, 4 + r), 0.04) for r in range(R)])
+    s = fly.System(data, fly.Box(tuple(ex)), ids, replicas=R)
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(pos)
+    pot = fly.Generic(data)
+    E = pot.energy(nl)
+    g = pot.gradient(nl)
+    osys = oracle_lib.System(otab, ex)
+    for r in range(R):
+        _compare_lists(fly, nl, osys, otab.rcut, pos[r], replica=r)
+        Eo = osys.energy(ids, 2)
+        assert abs(E[r] - Eo) <= 1e-10 * abs(Eo)
+        assert np.abs(g[r] - osys.gradient(ids, np.zeros(len(ids), np.uint8), 2)).max() < 1e-9
+    s.close()
+
+
+def test_partially_periodic_and_fuzz_boxes(gpu, otab, oracle_lib):
+    """Orthorhombic slice of tests/neigh/list.cpp:167-208: random boxes, random periodicity, r = min width / 3."""
+    fly, ctx, data = gpu
+    rng = np.random.default_rng(1334)
+    for trial in range(12):
+        ex = 1 + 9 * rng.random(3) + rng.random(3)
+        periodic = tuple(bool(x) for x in rng.random(3) < 0.5)
+        n = int(rng.integers(100, 1000))
+        pos = rng.random((n, 3)) * ex
+        r_cut = ex.min() / 3
+        ids = np.zeros(n, np.uint32)
+        s = fly.System(data, fly.Box(tuple(ex), periodic), ids)
+        nl = fly.List(s, r_cut)
+        nl.rebuild(pos)
+        osys = oracle_lib.System(otab, ex, periodic)
+        _compare_lists(fly, nl, osys, r_cut, pos)
+        s.close()
+
+
+def test_errors(gpu, oracle_lib):
+    fly, ctx, data = gpu
+    pos, ex, ids = bcc_vacancy(4, hydrogen=False)
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    pot = fly.Generic(data)
+    nl = fly.List(s, 3.0)  # list radius below the potential cut-off: for_neighbours throws (list.hpp:141-143)
+    nl.rebuild(pos)
+    with pytest.raises(fly.OflyError):
+        pot.gradient(nl)
+    with pytest.raises(fly.OflyError):
+        fly.List(s, 100.0).rebuild(pos)  # r_cut too big for the box (hypergrid.hpp:46)
+    # two atoms on top of each other: rho overruns the F table -> Spline::OutOfBounds
+    bad = pos.copy()
+    bad[1:40] = bad[0] + np.linspace(0.01, 0.4, 39)[:, None]
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(bad)
+    with pytest.raises(fly.OutOfBounds):
+        pot.gradient(nl)
+    with pytest.raises(fly.OflyError):
+        fly.System(data, fly.Box(tuple(ex)), np.full(10, 7, np.uint32))  # TypeID outside the table
+    s.close()
