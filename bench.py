@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the force-evaluation hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1], "C2"): bcc Fe 20x20x20 (a = 2.8553), one vacancy, one H -> 16 000 atoms;
+a batch of 64 concurrent dimer saddle searches started from Master::perturb-style states around the H atom.
+One *step* = one Dimer::find_sp over the whole batch (reference default options), i.e. every neighbour
+rebuild/update, EAM gradient, rotor and L-BFGS update of 64 searches, all inside one persistent kernel.
+
+  value  = EAM atom-gradient evaluations / s inside the step, inputs resident in HBM (ofly_dimer_find_sp_dev)
+  e2e    = same metric through the host-pointer C-ABI call (ofly_dimer_find_sp): pinned host inputs are copied
+           to the device and positions/axes/exit codes are copied back inside the timed region
+  roofline: algorithmic bytes (8 n + 64 per atom-gradient eval, n = measured mean stored neighbours) over the
+           CUDA-event duration of the persistent search kernel, against MEASURED_PEAKS.json's HBM figure
+  cpu_baseline / --impl reference: the CPU oracle built with the reference's flags, all host cores, one
+           single-threaded search per core exactly like saddle::Master (src/saddle/find.cpp:698,990)
+
+N > 1 (torchrun): replicas shard by rank with no collective on the data path; every rank runs its own
+64-search batch (weak scaling); only the timing and the counters are reduced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WEN = os.path.join(ROOT, "data", "wen.eam.fs")
+CELLS, LATTICE, REPLICAS = 20, 2.8553, 64
+METRIC, UNIT = "eam_atom_gradient_evals_per_s", "atom-evals/s"
+WORKLOAD = "C2: bcc Fe 20^3 (a=2.8553) - 1 vacancy + 1 H = 16000 atoms, Wen Fe-H EAM, 64 concurrent dimer searches (Dimer::find_sp, default options)"
+CPU_SAMPLE_MAX_STEPS = 40  # translation steps per CPU search in the bounded sample
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(seed: int):
+    from openfly_b200 import inputs
+
+    pos, ex, ids = inputs.iron_hydrogen_cell(CELLS, LATTICE, remove=(1,), hydrogen=True)
+    return pos, ex, ids, seed
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import ctypes as C
+
+    import torch
+
+    from openfly_b200 import capi, fly, inputs
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    ctx = fly.Context(local)
+    lib = ctx.lib
+    data = fly.DataEAM(ctx, WEN)
+    pot = fly.Generic(data)
+    pos, ex, ids, _ = build_inputs(args.seed)
+    N, R = len(ids), REPLICAS
+    box = fly.Box(tuple(ex))
+
+    # set-up (untimed): relax the cell, draw this rank's start states
+    s1 = fly.System(data, box, ids, replicas=1)
+    rmin, _, failed, _ = fly.LBFGS().minimise(s1, pos, pot)
+    assert not failed[0], "set-up minimisation did not converge"
+    rmin = rmin[0]
+    s1.close()
+    P, A = inputs.perturbed_batch(rmin, ex, N - 1, R, args.seed + 1000 * rank)
+
+    sysR = fly.System(data, box, ids, replicas=R)
+    nbytes = P.nbytes
+    d_pos, d_axis, d_outp, d_outa = (ctx.alloc(nbytes) for _ in range(4))
+    d_min = ctx.alloc(rmin.nbytes)
+    d_code, d_cnt = ctx.alloc(4 * R), ctx.alloc(8 * 4 * R)
+    ctx.upload(d_pos, P), ctx.upload(d_axis, A), ctx.upload(d_min, rmin)
+    dopt, ropt = fly.dimer_options(), fly.rotor_options()
+    theta_tol = np.pi / 6  # empty SP cache, first batch of an environment (find.cpp:692 at tot = 0)
+
+    def step_dev():
+        capi.check(lib.ofly_dimer_find_sp_dev(sysR.h, C.byref(dopt), C.byref(ropt), d_pos, d_axis, d_min, None, 0, theta_tol, 0,
+                                              d_outp, d_outa, d_code, d_cnt))
+
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_dev()
+        ev1.record(stream)
+        barrier()
+    launches = ctx.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+
+    cnt = np.zeros((R, 4), dtype=np.int64)
+    code = np.zeros(R, dtype=np.int32)
+    ctx.download(cnt, d_cnt), ctx.download(code, d_code)
+    evals_step = int(cnt[:, 0].sum())  # gradient evaluations of one step on this rank
+    nbar = fly.List(sysR, 0).mean_count()
+
+    # end-to-end leg: host buffers in, host buffers out, through the reference-facing call
+    hP, hA = torch.from_numpy(P).pin_memory(), torch.from_numpy(A).pin_memory()
+    oP, oA = torch.empty_like(hP).pin_memory(), torch.empty_like(hA).pin_memory()
+    hcode, hcnt = np.zeros(R, dtype=np.int32), np.zeros((R, 4), dtype=np.int64)
+    _dp, _ip, _lp = capi._dp, capi._ip, capi._lp
+
+    def step_host():
+        capi.check(lib.ofly_dimer_find_sp(sysR.h, C.byref(dopt), C.byref(ropt), C.cast(hP.data_ptr(), _dp), C.cast(hA.data_ptr(), _dp),
+                                          capi.ptr(rmin, _dp), None, 0, theta_tol, 0, C.cast(oP.data_ptr(), _dp),
+                                          C.cast(oA.data_ptr(), _dp), capi.ptr(hcode, _ip), capi.ptr(hcnt, _lp)))
+
+    step_host()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(hcode, code), "host-buffer and device-resident calls disagree"
+
+    # isolated gradient launches on the resident batch (roofline study of the pair kernels)
+    grad_leg = None
+    if world == 1:
+        r_list = data.rcut() + 2 * ropt.delta_r
+        r_list += max(dopt.skin_frac ** (1 / 3) - 1, 0) * r_list
+        capi.check(lib.ofly_neigh_rebuild_dev(sysR.h, r_list, d_pos))
+        iters = 20
+        for _ in range(3):
+            capi.check(lib.ofly_eam_gradient_dev(sysR.h, d_outp))
+        ctx.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(iters):
+            capi.check(lib.ofly_eam_gradient_dev(sysR.h, d_outp))
+        g1.record(stream)
+        ctx.synchronize()
+        gms = g0.elapsed_time(g1) / iters
+        n2 = fly.List(sysR, 0).mean_count()
+        grad_leg = {"atom_evals_per_s": R * N / (gms * 1e-3), "ms_per_eval_batch": gms, "mean_neighbours": n2,
+                    "kernels": "k_eam_rho + k_eam_force (grid kernels, 64 x 16000 atoms per launch pair)"}
+
+    # reduce over ranks: max time, sum of work
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s = float(t[0]), float(t[1])
+        w = torch.tensor([evals_step, R, int((code == 0).sum())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        evals_all, searches_all, success_all = float(w[0]), float(w[1]), float(w[2])
+    else:
+        evals_all, searches_all, success_all = float(evals_step), float(R), float((code == 0).sum())
+
+    if rank == 0:
+        sec = ms_total * 1e-3
+        value = evals_all * N * args.steps / sec
+        e2e = evals_all * N * e2e_steps / e2e_s
+        peak, peak_src = peaks()
+        b_alg = 8 * nbar + 64
+        # one launch of k_search = one step of this rank; per-rank algorithmic bytes / per-launch duration
+        achieved = (evals_step * N * b_alg) / (sec / args.steps) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "atoms": N, "replicas_per_gpu": R, "l2": "working set (neighbour rows 64x16000x~64x4 B + vectors) exceeds the 126 MB L2; no explicit flush",
+                       "seed": args.seed},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * nbytes + rmin.nbytes),
+                    "d2h_bytes_per_step": int(2 * nbytes + 4 * R + 32 * R), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "dimer_searches_per_s": searches_all * args.steps / sec,
+            "successful_saddles_per_s": success_all * args.steps / sec,
+            "gradient_evals_per_search": evals_all / searches_all,
+            "exit_codes": {str(k): int((code == k).sum()) for k in sorted(set(code.tolist()))},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_search (persistent, one launch per step)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_atom_eval": b_alg, "mean_neighbours": nbar,
+                         "note": "fp64 pipe co-limits this path (DESIGN.md); traffic from the ncu capture in profiles/"},
+            "clocks": clocks.summary(),
+        }
+        if grad_leg:
+            grad_leg["roofline_frac"] = grad_leg["atom_evals_per_s"] * (8 * grad_leg["mean_neighbours"] + 64) / 1e9 / peak
+            out["gradient_kernel"] = grad_leg
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(rmin, ex, ids, P, A, steps=1)
+        print(json.dumps(out), flush=True)
+
+    sysR.close(), data.close(), ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+def oracle_fast_lib():
+    """The oracle built with the reference's flags (-O3 -march=native) for THIS host when g++ is present,
+    else the prebuilt x86-64-v3 file that travelled with the repository."""
+    from oracle import oracle as O
+
+    src = os.path.join(ROOT, "oracle", "capi.cpp")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    out = os.path.join(tempfile.gettempdir(), f"liboracle_native_{os.getuid()}.so")
+    try:
+        subprocess.run([cxx, "-std=c++17", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", out, src], check=True,
+                       capture_output=True, timeout=300)
+        return O, out, "-O3 -march=native -fopenmp (reference CMakePresets flags), built on this host"
+    except Exception:  # noqa: BLE001
+        return O, None, "-O3 -march=x86-64-v3 -fopenmp (prebuilt)"
+
+
+def cpu_baseline(rmin, ex, ids, P, A, steps: int):
+    O, path, flags = oracle_fast_lib()
+    tab = O.Tables(WEN, fast=True, libpath=path)
+    osys = O.System(tab, ex)
+    cores = tab.L.max_threads()
+    fz = np.zeros(len(ids), np.uint8)
+    iopt = O.DIMER_IOPT.copy()
+    iopt[1] = CPU_SAMPLE_MAX_STEPS
+    n = cores
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, _, code, cnt = osys.find_sp_batch(P[:n], A[:n], ids, fz, rmin, threads=cores, iopt=iopt)
+        dt = time.perf_counter() - t0
+        v = float(cnt[:, 0].sum()) * len(ids) / dt
+        best = v if best is None else max(best, v)
+    return {"value": best, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": f"{n} of the 64 C2 searches (one single-threaded search per core, as saddle::Master), each cut at "
+                      f"max_steps={CPU_SAMPLE_MAX_STEPS}; oracle flags: {flags}"}
+
+
+def run_reference(args):
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    from openfly_b200 import inputs
+
+    O, path, flags = oracle_fast_lib()
+    tab = O.Tables(WEN, fast=True, libpath=path)
+    pos, ex, ids, _ = build_inputs(args.seed)
+    N = len(ids)
+    osys = O.System(tab, ex)
+    cores = tab.L.max_threads()
+    fz = np.zeros(N, np.uint8)
+    rmin, _, failed, _ = osys.minimise(pos, ids, fz, threads=cores)
+    assert not failed
+    P, A = inputs.perturbed_batch(rmin, ex, N - 1, cores, args.seed)
+    iopt = O.DIMER_IOPT.copy()
+    iopt[1] = CPU_SAMPLE_MAX_STEPS
+
+    def step():
+        _, _, code, cnt = osys.find_sp_batch(P, A, ids, fz, rmin, threads=cores, iopt=iopt)
+        return int(cnt[:, 0].sum())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    evals = 0
+    for _ in range(args.steps):
+        evals += step()
+    dt = time.perf_counter() - t0
+    value = evals * N / dt
+    sample = (f"{cores} of the 64 C2 searches per step (one single-threaded search per core, as saddle::Master), each cut at "
+              f"max_steps={CPU_SAMPLE_MAX_STEPS}; oracle flags: {flags}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "atoms": N, "seed": args.seed},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference itself cannot be built here (Eigen/fmt/cereal/nauty/KIM-API absent, DESIGN.md); this is the CPU oracle port",
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seed", type=int, default=1334)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
