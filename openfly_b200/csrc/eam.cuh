@@ -12,7 +12,7 @@
 // correction (fast_rsqrt) instead of an IEEE sqrt and an IEEE division.
 #pragma once
 
-#include "device_common.cuh"
+#include "neigh.cuh"
 
 namespace ofly {
 
@@ -124,40 +124,57 @@ namespace ofly {
     return deriv ? spline_fp(k, x0) : spline_f(k, x0);
   }
 
-  // ---- grid-wide kernels -----------------------------------------------------------------------
+  // ---- grid kernels ------------------------------------------------------------------------------
+  // Same selection scheme as the neighbour kernels (neigh.cuh, struct Sel): one work item is a tile
+  // of 256/G consecutive atoms of one selected replica; blocks stride over the items, so the launch
+  // geometry does not depend on how many replicas are still searching.
 
+  // Pass 1: rho and F'(rho) -> pos4[].w
   template <int G>
-  static __global__ void __launch_bounds__(256) k_eam_rho(BatchDev B, TablesDev T) {
-    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
-    int lane = threadIdx.x % G;
-    if (g >= (size_t)B.R * B.N) return;  // whole sub-warps leave together
-    int r = (int)(g / B.N), i = (int)(g % B.N);
-    bool oob = false;
-    double rho = eam_rho_atom<G, false>(B, T, r, i, lane, nullptr, oob);
-    if (lane == 0) {
-      double fp = embed(T, B.type[i], rho, true, oob);
-      reinterpret_cast<double *>(B.pos4 + (size_t)r * B.N + i)[3] = fp;
+  static __global__ void __launch_bounds__(256) k_eam_rho(BatchDev B, TablesDev T, Sel S) {
+    constexpr int kTile = 256 / G;
+    const int tiles = (B.N + kTile - 1) / kTile;
+    const long items = (long)(*S.count) * tiles;
+    const int lane = threadIdx.x % G;
+    for (long w = blockIdx.x; w < items; w += gridDim.x) {
+      const int r = S.list[w / tiles];
+      const int i = (int)(w % tiles) * kTile + threadIdx.x / G;
+      if (i >= B.N) continue;  // whole sub-warps leave together
+      bool oob = false;
+      double rho = eam_rho_atom<G, false>(B, T, r, i, lane, nullptr, oob);
+      if (lane == 0) {
+        double fp = embed(T, B.type[i], rho, true, oob);
+        reinterpret_cast<double *>(B.pos4 + (size_t)r * B.N + i)[3] = fp;
+      }
+      if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
-    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
   }
 
+  // Pass 2: gradient of replica r -> out + r * stride + offset[r * offset_stride] (offset may be null).
+  // The search keeps, per replica, the slot its next gradient belongs in (g0, g1, g1' of the rotor).
   template <int G>
-  static __global__ void __launch_bounds__(256) k_eam_force(BatchDev B, TablesDev T, double *__restrict__ out) {
-    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
-    int lane = threadIdx.x % G;
-    if (g >= (size_t)B.R * B.N) return;
-    int r = (int)(g / B.N), i = (int)(g % B.N);
-    bool oob = false;
-    double gx = 0, gy = 0, gz = 0;
-    if (!B.frozen[i]) eam_force_atom<G>(B, T, r, i, lane, gx, gy, gz, oob);
-    if (lane == 0) {
-      double *o = out + ((size_t)r * B.N + i) * 3;
-      o[0] = gx, o[1] = gy, o[2] = gz;
+  static __global__ void __launch_bounds__(256) k_eam_force(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
+                                                            const unsigned long long *__restrict__ offset, size_t offset_stride) {
+    constexpr int kTile = 256 / G;
+    const int tiles = (B.N + kTile - 1) / kTile;
+    const long items = (long)(*S.count) * tiles;
+    const int lane = threadIdx.x % G;
+    for (long w = blockIdx.x; w < items; w += gridDim.x) {
+      const int r = S.list[w / tiles];
+      const int i = (int)(w % tiles) * kTile + threadIdx.x / G;
+      if (i >= B.N) continue;
+      bool oob = false;
+      double gx = 0, gy = 0, gz = 0;
+      if (!B.frozen[i]) eam_force_atom<G>(B, T, r, i, lane, gx, gy, gz, oob);
+      if (lane == 0) {
+        double *o = out + (size_t)r * stride + (offset ? (size_t)offset[(size_t)r * offset_stride] : 0) + (size_t)i * 3;
+        o[0] = gx, o[1] = gy, o[2] = gz;
+      }
+      if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
-    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
   }
 
-  // Per-atom energy e_i = 0.5 sum V + F(rho) into scratch[R][N].
+  // Per-atom energy e_i = 0.5 sum V + F(rho) into scratch[R][N] (all replicas).
   template <int G>
   static __global__ void __launch_bounds__(256) k_eam_energy_atoms(BatchDev B, TablesDev T, double *__restrict__ scratch) {
     size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;

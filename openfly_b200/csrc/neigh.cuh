@@ -163,7 +163,16 @@ namespace ofly {
     st256(p, v);
   }
 
-  // ---- grid-wide kernels (stand-alone List::rebuild / List::update calls) -----------------------
+  // ---- grid kernels ------------------------------------------------------------------------------
+  // Every kernel works on a *selection* of replicas read from device memory (list + count), with a
+  // grid-stride loop over (selected replica, item). The stand-alone List::rebuild call selects all
+  // replicas; the lock-step search (search.cuh) selects the replicas whose skin was used up this
+  // tick -- the launch geometry is fixed (graph-capturable) and a launch with an empty selection
+  // returns at once.
+  struct Sel {
+    const int *list;   // replica ids
+    const int *count;  // number of entries
+  };
 
   static __global__ void k_nb_zero(BatchDev B) {
     size_t n = (size_t)B.R * B.grid.ncells;
@@ -171,11 +180,13 @@ namespace ofly {
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < (size_t)B.R; t += (size_t)gridDim.x * blockDim.x) B.fault[t] = 0;
   }
 
-  static __global__ void k_nb_canon_count(BatchDev B, const double *__restrict__ pos) {
-    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= (size_t)B.R * B.N) return;
-    int r = (int)(t / B.N), i = (int)(t % B.N);
-    nb_canon_count(B, pos + (size_t)r * 3 * B.N, r, i);
+  // pos: base of the callers' position arrays; replica r's [3N] array starts at pos + r * stride.
+  static __global__ void __launch_bounds__(256) k_nb_canon_count(BatchDev B, Sel S, const double *__restrict__ pos, size_t stride) {
+    const size_t total = (size_t)(*S.count) * B.N;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+      int r = S.list[t / B.N], i = (int)(t % B.N);
+      nb_canon_count(B, pos + (size_t)r * stride, r, i);
+    }
   }
 
   // Step 2 by one CTA: exclusive scan of the replica's histogram into cell_start[0..ncells].
@@ -221,35 +232,41 @@ namespace ofly {
     __syncthreads();
   }
 
-  static __global__ void __launch_bounds__(1024) k_nb_scan(BatchDev B) {
+  static __global__ void __launch_bounds__(1024) k_nb_scan(BatchDev B, Sel S) {
     __shared__ int sm[33];
-    nb_scan_block(B, blockIdx.x, sm);
+    const int n = *S.count;
+    for (int a = blockIdx.x; a < n; a += gridDim.x) nb_scan_block(B, S.list[a], sm);
   }
 
-  static __global__ void k_nb_scatter(BatchDev B) {
-    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= (size_t)B.R * B.N) return;
-    nb_scatter(B, (int)(t / B.N), (int)(t % B.N));
-  }
-
-  static __global__ void k_nb_sort_cells(BatchDev B) {
-    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= (size_t)B.R * B.grid.ncells) return;
-    nb_sort_cell(B, (int)(t / B.grid.ncells), (int)(t % B.grid.ncells));
-  }
-
-  template <int G>
-  static __global__ void __launch_bounds__(256) k_nb_build(BatchDev B) {
-    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
-    int lane = threadIdx.x % G;
-    // whole sub-warps are in or out together (grid is sized in units of G)
-    if (g >= (size_t)B.R * B.N) {
-      g = (size_t)B.R * B.N - 1;  // tail sub-warps redo the last atom (identical writes) instead of exiting
+  static __global__ void __launch_bounds__(256) k_nb_scatter(BatchDev B, Sel S) {
+    const size_t total = (size_t)(*S.count) * B.N;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+      nb_scatter(B, S.list[t / B.N], (int)(t % B.N));
     }
-    nb_build_atom<G>(B, (int)(g / B.N), (int)(g % B.N), lane);
   }
 
-  static __global__ void k_nb_update(BatchDev B, const double *__restrict__ delta) {
+  static __global__ void __launch_bounds__(128) k_nb_sort_cells(BatchDev B, Sel S) {
+    const size_t total = (size_t)(*S.count) * B.grid.ncells;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+      nb_sort_cell(B, S.list[t / B.grid.ncells], (int)(t % B.grid.ncells));
+    }
+  }
+
+  // One work item = one tile of 256/G consecutive atoms of one selected replica.
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_nb_build(BatchDev B, Sel S) {
+    constexpr int kTile = 256 / G;
+    const int tiles = (B.N + kTile - 1) / kTile;
+    const long items = (long)(*S.count) * tiles;
+    const int lane = threadIdx.x % G;
+    for (long w = blockIdx.x; w < items; w += gridDim.x) {
+      int r = S.list[w / tiles];
+      int i = (int)(w % tiles) * kTile + threadIdx.x / G;
+      if (i < B.N) nb_build_atom<G>(B, r, i, lane);  // whole sub-warps are in or out together
+    }
+  }
+
+  static __global__ void __launch_bounds__(256) k_nb_update(BatchDev B, const double *__restrict__ delta) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= (size_t)B.R * B.N) return;
     int r = (int)(t / B.N), i = (int)(t % B.N);
