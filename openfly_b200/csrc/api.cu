@@ -65,6 +65,12 @@ namespace ofly {
     OFLY_CUDA(cudaGetLastError());
   }
 
+  // Grid of a grid-stride kernel: enough blocks to fill the chip `per_sm` deep, never more than the work.
+  static unsigned stride_grid(ofly_ctx *ctx, size_t blocks_of_work, int per_sm) {
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(blocks_of_work, (size_t)ctx->sm_count * per_sm));
+  }
+  static Sel all_replicas(ofly_batch *b) { return Sel{b->sel_all.p, b->sel_all.p + b->R}; }
+
   // ---- grid set-up: HyperGrid ctor (hypergrid.hpp:43-56) --------------------------------------------
   static void make_grid(ofly_batch *b, double r_list) {
     GridDev g{};
@@ -126,24 +132,31 @@ namespace ofly {
 
   void enqueue_rebuild(ofly_batch *b, const double *pos_dev) {
     ofly_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
     size_t atoms = (size_t)b->R * b->N;
+    Sel all = all_replicas(b);
     launch(ctx, k_nb_zero, std::min<size_t>((size_t)b->R * b->d.grid.ncells, 1 << 20), 256, b->d);
-    launch(ctx, k_nb_canon_count, atoms, 256, b->d, pos_dev);
-    k_nb_scan<<<(unsigned)b->R, 1024, 0, ctx->stream>>>(b->d);
-    ctx->launches++;
-    launch(ctx, k_nb_scatter, atoms, 256, b->d);
-    launch(ctx, k_nb_sort_cells, (size_t)b->R * b->d.grid.ncells, 128, b->d);
-    switch (pick_group(ctx, (long)atoms)) {
+    k_nb_canon_count<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(b->d, all, pos_dev, (size_t)3 * b->N);
+    k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(b->d, all);
+    k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(b->d, all);
+    k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * b->d.grid.ncells + 127) / 128, 16), 128, 0, st>>>(b->d, all);
+    const int G = pick_group(ctx, (long)atoms);
+    const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), 8);
+    switch (G) {
       case 32:
-        launch(ctx, k_nb_build<32>, atoms * 32, 256, b->d);
+        k_nb_build<32><<<gg, 256, 0, st>>>(b->d, all);
         break;
       case 16:
-        launch(ctx, k_nb_build<16>, atoms * 16, 256, b->d);
+        k_nb_build<16><<<gg, 256, 0, st>>>(b->d, all);
+        break;
+      case 8:
+        k_nb_build<8><<<gg, 256, 0, st>>>(b->d, all);
         break;
       default:
-        launch(ctx, k_nb_build<8>, atoms * 8, 256, b->d);
+        k_nb_build<4><<<gg, 256, 0, st>>>(b->d, all);
         break;
     }
+    ctx->launches += 5;
     OFLY_CUDA(cudaGetLastError());
   }
 
@@ -173,26 +186,33 @@ namespace ofly {
 
   void enqueue_gradient(ofly_batch *b, double *grad_dev) {
     ofly_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
     size_t atoms = (size_t)b->R * b->N;
     TablesDev const &T = b->tables->dev;
-    switch (pick_group(ctx, (long)atoms)) {
+    Sel all = all_replicas(b);
+    const size_t stride = (size_t)3 * b->N;
+    const int G = pick_group(ctx, (long)atoms);
+    const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), 8);
+    switch (G) {
       case 32:
-        launch(ctx, k_eam_rho<32>, atoms * 32, 256, b->d, T);
-        launch(ctx, k_eam_force<32>, atoms * 32, 256, b->d, T, grad_dev);
+        k_eam_rho<32><<<gg, 256, 0, st>>>(b->d, T, all);
+        k_eam_force<32><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
         break;
       case 16:
-        launch(ctx, k_eam_rho<16>, atoms * 16, 256, b->d, T);
-        launch(ctx, k_eam_force<16>, atoms * 16, 256, b->d, T, grad_dev);
+        k_eam_rho<16><<<gg, 256, 0, st>>>(b->d, T, all);
+        k_eam_force<16><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
         break;
       case 8:
-        launch(ctx, k_eam_rho<8>, atoms * 8, 256, b->d, T);
-        launch(ctx, k_eam_force<8>, atoms * 8, 256, b->d, T, grad_dev);
+        k_eam_rho<8><<<gg, 256, 0, st>>>(b->d, T, all);
+        k_eam_force<8><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
         break;
       default:
-        launch(ctx, k_eam_rho<4>, atoms * 4, 256, b->d, T);
-        launch(ctx, k_eam_force<4>, atoms * 4, 256, b->d, T, grad_dev);
+        k_eam_rho<4><<<gg, 256, 0, st>>>(b->d, T, all);
+        k_eam_force<4><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
         break;
     }
+    ctx->launches += 2;
+    OFLY_CUDA(cudaGetLastError());
   }
 
   // used by search_api.cu
@@ -364,6 +384,12 @@ int ofly_batch_create(ofly_ctx *ctx, ofly_tables *tables, const double extents[3
       OFLY_CUDA(cudaMemcpy(b->type.p, b->type_host.data(), (size_t)n_atoms, cudaMemcpyHostToDevice));
       OFLY_CUDA(cudaMemcpy(b->frozen.p, fz.data(), (size_t)n_atoms, cudaMemcpyHostToDevice));
       b->pos4.reserve(atoms), b->cnt.reserve(atoms), b->cell_of.reserve(atoms), b->fault.reserve((size_t)b->R);
+      {
+        std::vector<int> iota((size_t)b->R + 1);
+        for (long r = 0; r <= b->R; r++) iota[(size_t)r] = (int)r;  // last entry doubles as the count
+        b->sel_all.reserve(iota.size());
+        OFLY_CUDA(cudaMemcpy(b->sel_all.p, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice));
+      }
       OFLY_CUDA(cudaMemset(b->fault.p, 0, sizeof(int) * (size_t)b->R));
       OFLY_CUDA(cudaMemset(b->cnt.p, 0, sizeof(int) * atoms));
       b->d.N = (int)b->N, b->d.R = (int)b->R, b->d.K = 0, b->d.img_cap = 0;
@@ -381,7 +407,7 @@ void ofly_batch_destroy(ofly_batch *b) {
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->cell_items.release();
-  b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release();
+  b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release(), b->sel_all.release();
   b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();
   ofly_tables_release(b->tables);
   delete b;
@@ -524,8 +550,11 @@ int ofly_eam_energy(ofly_batch *b, double *energy_host) {
       case 16:
         launch(b->ctx, k_eam_energy_atoms<16>, atoms * 16, 256, b->d, T, b->scratch.p);
         break;
-      default:
+      case 8:
         launch(b->ctx, k_eam_energy_atoms<8>, atoms * 8, 256, b->d, T, b->scratch.p);
+        break;
+      default:
+        launch(b->ctx, k_eam_energy_atoms<4>, atoms * 4, 256, b->d, T, b->scratch.p);
         break;
     }
     k_reduce_rows<<<(unsigned)b->R, 1024, 0, b->ctx->stream>>>(b->scratch.p, (int)b->N, b->scratch.p + atoms);

@@ -1,20 +1,30 @@
-// Device-resident minimiser and dimer saddle search: one persistent team (a thread-block cluster of
-// C CTAs) owns one replica for the WHOLE search, so there is no per-step host round trip and replicas
-// with different iteration counts, rebuild decisions and exits never wait for each other. Teams pull
-// replicas from a device queue until the batch is drained.
+// Device-resident minimiser and dimer saddle search, batched in lock-step over replicas.
 //
 // Restates, per replica:
 //   minimise::LBFGS::minimise        src/minimise/LBFGS/lbfgs.cpp:29-115
 //   minimise::StepLBFGS::newton_step src/minimise/LBFGS/lbfgs_core.cpp:29-87
 //   saddle::Rotor::eff_gradient      src/saddle/rotor.cpp:33-164
 //   saddle::Dimer::find_sp           src/saddle/dimer.cpp:28-171
-// calling the same neighbour (neigh.cuh) and EAM (eam.cuh) device functions as the grid kernels.
 //
-// Vector algebra: every 3N-vector op is one strided pass by the whole team; dot products are fused
-// into the pass that produces their operand (the L-BFGS two-loop costs one pass + one reduction per
-// history pair) and reduced warp-shuffle -> shared memory -> (cluster: distributed shared memory) in a
-// fixed order, so all threads of the team obtain bit-identical scalars and take the same branches
-// without any broadcast. Per-replica scalars (trust, acc, curvature, counters) live in registers.
+// Every algorithm above is a chain of 3N-vector passes punctuated by EAM gradient evaluations (and,
+// when the skin is used up, a neighbour rebuild). The gradient is the expensive, embarrassingly
+// parallel part, so the batch advances in *ticks*: in one tick every still-searching replica runs its
+// own vector algebra up to its next gradient request (k_segment, one team = one CTA or one cluster of
+// CTAs per replica; replicas may be at completely different places of the algorithm), then ONE set of
+// grid kernels (neigh.cuh / eam.cuh) rebuilds the lists of the replicas that asked for it and
+// evaluates the gradient of all active replicas with the whole chip. A tick is a fixed sequence of
+// eight kernel nodes; the host enqueues it as a CUDA graph whose body repeats on the device (WHILE
+// conditional node) until no replica is active -- no per-step host round trip, no host-side branch.
+// Finished replicas simply drop out of the selection lists, so the chip stays full until the last
+// search ends instead of idling behind the slowest one.
+//
+// Vector algebra: every pass is strided over the team; dot products are fused into the pass that
+// produces their operand (the L-BFGS two-loop costs one pass + one reduction per history pair) and
+// reduced warp-shuffle -> shared memory -> (cluster: st.async posts into every peer's shared memory,
+// counted in by mbarriers) in a fixed order, so all threads of a team obtain bit-identical scalars and
+// take the same branches without a broadcast. Every pass is indexed by vector component, so a thread
+// only re-reads data it wrote itself and no pass needs a memory fence or a cluster barrier.
+// Per-replica scalars (phase, trust, acc, curvature, L-BFGS rho_j, counters) persist in RepState.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -26,14 +36,41 @@ namespace ofly {
 
   namespace cg = cooperative_groups;
 
-  constexpr int kSearchThreads = 512;
-  constexpr int kSearchGroup = 8;  // lanes per atom inside the search kernel
-  constexpr int kMaxHist = 16;     // upper bound on L-BFGS memory
-  constexpr int kMaxRed = 8;       // values per fused reduction
+  constexpr int kMaxHist = 16;  // upper bound on L-BFGS memory
+  constexpr int kMaxRed = 8;    // values per fused reduction
 
   // Exit / status codes beyond the reference's enums.
   constexpr int kStatusOutOfBounds = -5;
   constexpr int kStatusCapacity = -6;
+  constexpr int kStatusUnfinished = -7;  // tick budget exhausted (should not happen)
+
+  // Where a replica resumes when its requested gradient has arrived.
+  enum Phase : int { kInit = 0, kMinGrad = 1, kRotG0 = 2, kRotG1 = 3, kRotG1p = 4, kDone = 5 };
+
+  struct CoreState {  // StepLBFGS (lbfgs_core.hpp:101-118): history fill + rho_j
+    int k, pad;
+    double rho[kMaxHist];
+  };
+
+  struct RepState {
+    int phase, status;
+    int iter;     // translation / minimiser step index i
+    int rot_it;   // rotor iteration
+    int first;    // no step taken yet (first effective gradient / first gradient)
+    int need_rebuild;
+    unsigned long long gdst;  // offset (doubles) inside the replica's workspace for the next gradient
+    double trust, acc, convex_count, curv, mag_g;
+    double c_x0, b_1, theta_1;  // rotor scalars carried over the trial-gradient request
+    CoreState trans, rot;
+    long tally[4];  // grad_evals, rebuilds, updates, steps
+  };
+
+  struct Control {
+    int n_active, n_rebuild;  // entries in the selection lists for the grid kernels of this tick
+    int ticket;               // teams that have finished their segment in this tick
+    int tick;
+    int pad[4];
+  };
 
   struct SearchParams {
     int mode;  // 0: LBFGS::minimise, 1: Dimer::find_sp
@@ -54,19 +91,63 @@ namespace ofly {
     double *pos_out, *axis_out, *grad_out;
     int *status;
     long *counters;  // [R][4] or null
-    double *ws;      // per-team workspace
+    // engine
+    double *ws;  // [R][ws_stride] vectors
     size_t ws_stride;
-    int *queue;
+    RepState *state;  // [R]
+    Control *ctl;
+    int *active, *rebuild;  // [R] selection lists
+    int max_ticks;
+    int use_cond;
+    cudaGraphConditionalHandle cond;
   };
 
-  // ---- team = cluster of C CTAs ------------------------------------------------------------------
+  // ---- team = one CTA or a cluster of C CTAs ------------------------------------------------------
+  // Cluster-wide sums go through distributed shared memory without a cluster barrier: every CTA posts
+  // its partial sums into all peers' slots with st.async, which also counts the bytes in on the
+  // receiver's mbarrier; a CTA only waits on its *own* mbarrier (CTA-scope acquire). A cluster-scope
+  // barrier would invalidate the L1 on every reduction (and there are 20-40 per segment).
+  __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, int cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+  }
+  __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+  }
+  // 8-byte store into a peer CTA's shared memory that completes 8 bytes on that CTA's mbarrier.
+  __device__ __forceinline__ void dsmem_post(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+  }
+
   template <int C>
   struct Team {
     int tid, nthreads, rank;
-    double *red;  // shared: [2][C][kMaxRed] cluster slots, then [2][32][kMaxRed] warp partials
+    double *red;    // shared: [2][C][kMaxRed] cluster slots, then [2][32][kMaxRed] warp partials
+    uint64_t *bar;  // shared: [2] mbarriers, one per slot buffer (clusters only)
     int parity = 0;
+    uint32_t phase = 0;  // bit p: parity the next wait on bar[p] looks for
 
-    __device__ Team(double *smem) : red(smem) {
+    __device__ Team(double *smem, uint64_t *bars) : red(smem), bar(bars) {
       if constexpr (C > 1) {
         rank = (int)cg::this_cluster().block_rank();
       } else {
@@ -76,12 +157,20 @@ namespace ofly {
       nthreads = C * blockDim.x;
     }
 
-    __device__ __forceinline__ void sync() {
+    // Once per kernel, by every CTA of the cluster, before the first reduce.
+    __device__ __forceinline__ void init() {
       if constexpr (C > 1) {
+        if (threadIdx.x == 0) {
+          mbar_init(bar, 1), mbar_init(bar + 1, 1);
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         cg::this_cluster().sync();
-      } else {
-        __syncthreads();
       }
+    }
+    // Before the CTAs of a cluster part ways: nobody's shared memory may go away while a peer's
+    // posts to it could still be in flight.
+    __device__ __forceinline__ void fini() {
+      if constexpr (C > 1) cg::this_cluster().sync();
     }
 
     // Sum NV values over the team; result (identical bits on every thread) overwrites v.
@@ -107,16 +196,17 @@ namespace ofly {
           v[q] = x;
         }
       } else {
+        uint64_t *mb = bar + parity;
         if (threadIdx.x < NV) {
           double x = 0;
           for (int k = 0; k < nw; k++) x += warp_part[k * kMaxRed + threadIdx.x];
-          cg::cluster_group cl = cg::this_cluster();
-          for (int c = 0; c < C; c++) {
-            double *remote = cl.map_shared_rank(slots, c);
-            remote[rank * kMaxRed + threadIdx.x] = x;
-          }
+          const uint32_t slot = smem_u32(slots + rank * kMaxRed + threadIdx.x), mbl = smem_u32(mb);
+#pragma unroll
+          for (int c = 0; c < C; c++) dsmem_post(map_to_cta(slot, c), x, map_to_cta(mbl, c));
         }
-        cg::this_cluster().sync();
+        if (threadIdx.x == 0) mbar_expect_tx(mb, C * NV * 8);
+        mbar_wait(mb, (phase >> parity) & 1u);
+        phase ^= 1u << parity;
 #pragma unroll
         for (int q = 0; q < NV; q++) {
           double x = 0;
@@ -131,63 +221,44 @@ namespace ofly {
 
   __host__ __device__ constexpr size_t team_smem_doubles(int C) { return 2 * (size_t)C * kMaxRed + 2 * 32 * kMaxRed; }
 
-  // ---- per-replica building blocks ------------------------------------------------------------------
-
-  // neigh::List::rebuild(x) by the team (same five steps as the grid kernels in neigh.cuh).
-  template <int C>
-  __device__ __noinline__ void team_rebuild(Team<C> &tm, const BatchDev &B, int r, const double *x, int *scan_smem) {
-    int *hist = B.cell_count + (size_t)r * B.grid.ncells;
-    for (int c = tm.tid; c < B.grid.ncells; c += tm.nthreads) hist[c] = 0;
-    tm.sync();
-    for (int i = tm.tid; i < B.N; i += tm.nthreads) nb_canon_count(B, x, r, i);
-    tm.sync();
-    if (tm.rank == 0) nb_scan_block(B, r, scan_smem);
-    tm.sync();
-    for (int i = tm.tid; i < B.N; i += tm.nthreads) nb_scatter(B, r, i);
-    tm.sync();
-    for (int c = tm.tid; c < B.grid.ncells; c += tm.nthreads) nb_sort_cell(B, r, c);
-    tm.sync();
-    constexpr int G = kSearchGroup;
-    const int lane = tm.tid % G, ngroups = tm.nthreads / G;
-    for (int i = tm.tid / G; i < B.N; i += ngroups) nb_build_atom<G>(B, r, i, lane);
-    tm.sync();
+  // One strided pass over n elements by the whole team. The passes are latency-bound (a few dozen
+  // elements per thread, each a round trip to L2/HBM), so all inputs of kPassUnroll elements are fetched
+  // before the first is used. body(t, v) sees v[k] = src[k][t]; a thread visits its elements in
+  // ascending t, so fused dot products accumulate in the same order whatever the unroll.
+  constexpr int kPassUnroll = 4;
+  template <int NIN, typename F>
+  __device__ __forceinline__ void team_pass(int tid, int nthreads, int n, const double *const (&src)[NIN], F &&body) {
+    for (int t0 = tid; t0 < n; t0 += kPassUnroll * nthreads) {
+      double v[kPassUnroll][NIN];
+#pragma unroll
+      for (int u = 0; u < kPassUnroll; u++) {
+        const int t = t0 + u * nthreads;
+        if (t < n) {
+#pragma unroll
+          for (int k = 0; k < NIN; k++) v[u][k] = src[k][t];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPassUnroll; u++) {
+        const int t = t0 + u * nthreads;
+        if (t < n) body(t, v[u]);
+      }
+    }
   }
 
-  // potential::EAM::gradient by the team; returns false if a spline table was overrun.
-  template <int C>
-  __device__ __noinline__ bool team_gradient(Team<C> &tm, const BatchDev &B, const TablesDev &T, int r, double *out) {
-    constexpr int G = kSearchGroup;
-    const int lane = tm.tid % G, ngroups = tm.nthreads / G;
-    bool oob = false;
-    for (int i = tm.tid / G; i < B.N; i += ngroups) {
-      double rho = eam_rho_atom<G, false>(B, T, r, i, lane, nullptr, oob);
-      if (lane == 0) reinterpret_cast<double *>(B.pos4 + (size_t)r * B.N + i)[3] = embed(T, B.type[i], rho, true, oob);
-    }
-    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
-    tm.sync();
-    for (int i = tm.tid / G; i < B.N; i += ngroups) {
-      double gx = 0, gy = 0, gz = 0;
-      if (!B.frozen[i]) eam_force_atom<G>(B, T, r, i, lane, gx, gy, gz, oob);
-      if (lane == 0) out[3 * i] = gx, out[3 * i + 1] = gy, out[3 * i + 2] = gz;
-    }
-    if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
-    tm.sync();
-    return (__ldcg(B.fault + r) & kFaultOutOfBounds) == 0;
-  }
-
-  // L-BFGS history of one optimiser (StepLBFGS, lbfgs_core.hpp:101-118).
+  // L-BFGS history of one optimiser: vectors in the replica's workspace, scalars in RepState.
   struct Core {
     double *prev_x, *prev_g, *step, *s, *y;  // s, y: [n][n3p]
+    CoreState *st;
     int n, k;
     size_t n3p;
-    double rho[kMaxHist], alpha[kMaxHist];
   };
 
   // StepLBFGS::newton_step: core.step <- H * g (lbfgs_core.cpp:29-87). Also returns step.step and
-  // step.w (w may be null) from the final pass.
+  // step.w (w may be null) from the final pass. `k` is advanced in the local copy; the caller stores it.
   template <int C>
-  __device__ __noinline__ void newton_step(Team<C> &tm, Core &c, const double *x, const double *g, int n3, const double *w, double &out_nrm2,
-                              double &out_dotw) {
+  __device__ __forceinline__ void newton_step(Team<C> &tm, Core &c, const double *x, const double *g, int n3, const double *w, double &out_nrm2,
+                                           double &out_dotw) {
     const int n = c.n;
     const int prev = c.k > 0 ? (c.k - 1) % n : 0;
     const int incur = c.k <= n ? 0 : c.k - n;
@@ -196,54 +267,60 @@ namespace ofly {
 
     if (c.k == 0) {  // identity Hessian: step = g
       double a[2] = {0, 0};
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        double gv = g[t];
-        c.prev_x[t] = x[t], c.prev_g[t] = gv, q[t] = gv;
-        a[0] = fma(gv, gv, a[0]);
-        if (w) a[1] = fma(gv, w[t], a[1]);
-      }
+      const double *const src[3] = {g, x, w ? w : g};
+      team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
+        c.prev_x[t] = v[1], c.prev_g[t] = v[0], q[t] = v[0];
+        a[0] = fma(v[0], v[0], a[0]);
+        if (w) a[1] = fma(v[0], v[2], a[1]);
+      });
       tm.reduce<2>(a);
       out_nrm2 = a[0], out_dotw = a[1];
       c.k = 1;
       return;
     }
 
-    double yy, d;
+    double yy, d, rho_prev;
     {  // newest pair (s, y), prev <- current, q <- g, first dot of loop 1
       double *s = c.s + (size_t)prev * c.n3p, *y = c.y + (size_t)prev * c.n3p;
       double a[3] = {0, 0, 0};
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        double xv = x[t], gv = g[t];
-        double sv = xv - c.prev_x[t], yv = gv - c.prev_g[t];
+      const double *const src[4] = {x, g, c.prev_x, c.prev_g};
+      team_pass<4>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[4]) {
+        double xv = v[0], gv = v[1];
+        double sv = xv - v[2], yv = gv - v[3];
         s[t] = sv, y[t] = yv, c.prev_x[t] = xv, c.prev_g[t] = gv, q[t] = gv;
         a[0] = fma(sv, yv, a[0]), a[1] = fma(yv, yv, a[1]), a[2] = fma(sv, gv, a[2]);
-      }
+      });
       tm.reduce<3>(a);
-      c.rho[prev] = 1.0 / fabs(a[0]);  // abs: never an ascent direction (lbfgs_core.cpp:50)
+      rho_prev = 1.0 / fabs(a[0]);  // abs: never an ascent direction (lbfgs_core.cpp:50)
+      if (tm.tid == 0) c.st->rho[prev] = rho_prev;
       yy = a[1], d = a[2];
     }
-    const double h0 = 1.0 / c.rho[prev] / yy;  // initial Hessian scaling (lbfgs_core.cpp:70)
+    const double h0 = 1.0 / rho_prev / yy;  // initial Hessian scaling (lbfgs_core.cpp:70)
 
+    double alpha_of[kMaxHist];
     // loop 1, newest -> oldest: alpha_j = rho_j s_j.q ; q -= alpha_j y_j   (dot for the next pair fused)
     for (int i = bound - 1; i >= 0; --i) {
       const int j = (i + incur) % n;
-      const double alpha = c.rho[j] * d;
-      c.alpha[j] = alpha;
+      const double rho_j = j == prev ? rho_prev : c.st->rho[j];
+      const double alpha = rho_j * d;
+      alpha_of[j] = alpha;
       const double *y = c.y + (size_t)j * c.n3p;
       double a[1] = {0};
       if (i > 0) {
         const double *sn = c.s + (size_t)((i - 1 + incur) % n) * c.n3p;
-        for (int t = tm.tid; t < n3; t += tm.nthreads) {
-          double qv = fma(-alpha, y[t], q[t]);
+        const double *const src[3] = {y, q, sn};
+        team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
+          double qv = fma(-alpha, v[0], v[1]);
           q[t] = qv;
-          a[0] = fma(sn[t], qv, a[0]);
-        }
+          a[0] = fma(v[2], qv, a[0]);
+        });
       } else {  // last pair: apply H0 and start loop 2 with the same y
-        for (int t = tm.tid; t < n3; t += tm.nthreads) {
-          double rv = fma(-alpha, y[t], q[t]) * h0;
+        const double *const src[2] = {y, q};
+        team_pass<2>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[2]) {
+          double rv = fma(-alpha, v[0], v[1]) * h0;
           q[t] = rv;
-          a[0] = fma(y[t], rv, a[0]);
-        }
+          a[0] = fma(v[0], rv, a[0]);
+        });
       }
       tm.reduce<1>(a);
       d = a[0];
@@ -251,25 +328,174 @@ namespace ofly {
     // loop 2, oldest -> newest: beta = rho_j y_j.r ; r += (alpha_j - beta) s_j
     for (int i = 0; i < bound; ++i) {
       const int j = (i + incur) % n;
-      const double coef = c.alpha[j] - c.rho[j] * d;
+      const double rho_j = j == prev ? rho_prev : c.st->rho[j];
+      const double coef = alpha_of[j] - rho_j * d;
       const double *s = c.s + (size_t)j * c.n3p;
       if (i + 1 < bound) {
         const double *yn = c.y + (size_t)((i + 1 + incur) % n) * c.n3p;
         double a[1] = {0};
-        for (int t = tm.tid; t < n3; t += tm.nthreads) {
-          double rv = fma(coef, s[t], q[t]);
+        const double *const src[3] = {s, q, yn};
+        team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
+          double rv = fma(coef, v[0], v[1]);
           q[t] = rv;
-          a[0] = fma(yn[t], rv, a[0]);
+          a[0] = fma(v[2], rv, a[0]);
+        });
+        tm.reduce<1>(a);
+        d = a[0];
+      } else {
+        double a[2] = {0, 0};
+        const double *const src[3] = {s, q, w ? w : q};
+        team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
+          double rv = fma(coef, v[0], v[1]);
+          q[t] = rv;
+          a[0] = fma(rv, rv, a[0]);
+          if (w) a[1] = fma(rv, v[2], a[1]);
+        });
+        tm.reduce<2>(a);
+        out_nrm2 = a[0], out_dotw = a[1];
+      }
+    }
+    c.k++;
+  }
+
+  // Same recursion with the running vector q held in registers: thread `tid` owns elements
+  // tid + e * nthreads, e < EPT, for the whole call, so a pass only streams the two history vectors it
+  // needs (all of a chunk's loads are in flight together) and q never round-trips through memory.
+  // Visiting order and arithmetic per element are those of newton_step: results are bit-identical.
+  // Requires n3 <= EPT * nthreads.
+  template <int C, int EPT>
+  __device__ __forceinline__ void newton_step_reg(Team<C> &tm, Core &c, const double *x, const double *g, int n3, const double *w,
+                                               double &out_nrm2, double &out_dotw) {
+    constexpr int CH = 8;  // elements whose loads are issued back to back
+    static_assert(EPT % CH == 0, "EPT must be a multiple of the chunk");
+    const int n = c.n;
+    const int prev = c.k > 0 ? (c.k - 1) % n : 0;
+    const int incur = c.k <= n ? 0 : c.k - n;
+    const int bound = c.k <= n ? c.k : n;
+    const int tid = tm.tid, nth = tm.nthreads;
+
+    if (c.k == 0) return newton_step(tm, c, x, g, n3, w, out_nrm2, out_dotw);  // identity Hessian: one pass
+
+    double q[EPT];
+    double yy, d, rho_prev;
+    {  // newest pair (s, y), prev <- current, q <- g, first dot of loop 1
+      double *s = c.s + (size_t)prev * c.n3p, *y = c.y + (size_t)prev * c.n3p;
+      double a[3] = {0, 0, 0};
+#pragma unroll
+      for (int e0 = 0; e0 < EPT; e0 += CH / 2) {
+        double xv[CH / 2], gv[CH / 2], px[CH / 2], pg[CH / 2];
+#pragma unroll
+        for (int u = 0; u < CH / 2; u++) {
+          const int t = tid + (e0 + u) * nth;
+          if (t < n3) xv[u] = x[t], gv[u] = g[t], px[u] = c.prev_x[t], pg[u] = c.prev_g[t];
+        }
+#pragma unroll
+        for (int u = 0; u < CH / 2; u++) {
+          const int t = tid + (e0 + u) * nth;
+          if (t < n3) {
+            double sv = xv[u] - px[u], yv = gv[u] - pg[u];
+            s[t] = sv, y[t] = yv, c.prev_x[t] = xv[u], c.prev_g[t] = gv[u];
+            q[e0 + u] = gv[u];
+            a[0] = fma(sv, yv, a[0]), a[1] = fma(yv, yv, a[1]), a[2] = fma(sv, gv[u], a[2]);
+          }
+        }
+      }
+      tm.reduce<3>(a);
+      rho_prev = 1.0 / fabs(a[0]);
+      if (tid == 0) c.st->rho[prev] = rho_prev;
+      yy = a[1], d = a[2];
+    }
+    const double h0 = 1.0 / rho_prev / yy;
+
+    double alpha_of[kMaxHist];
+    // loop 1, newest -> oldest
+    for (int i = bound - 1; i >= 0; --i) {
+      const int j = (i + incur) % n;
+      const double rho_j = j == prev ? rho_prev : c.st->rho[j];
+      const double alpha = rho_j * d;
+      alpha_of[j] = alpha;
+      const double *y = c.y + (size_t)j * c.n3p;
+      const double *sn = i > 0 ? c.s + (size_t)((i - 1 + incur) % n) * c.n3p : y;  // last pair: dot with the same y after H0
+      const bool last = i == 0;
+      double a[1] = {0};
+#pragma unroll
+      for (int e0 = 0; e0 < EPT; e0 += CH) {
+        double yv[CH], sv[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+          const int t = tid + (e0 + u) * nth;
+          if (t < n3) {
+            yv[u] = y[t];
+            sv[u] = last ? yv[u] : sn[t];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+          const int t = tid + (e0 + u) * nth;
+          if (t < n3) {
+            double qv = fma(-alpha, yv[u], q[e0 + u]);
+            if (last) qv *= h0;
+            q[e0 + u] = qv;
+            a[0] = fma(sv[u], qv, a[0]);
+          }
+        }
+      }
+      tm.reduce<1>(a);
+      d = a[0];
+    }
+    // loop 2, oldest -> newest
+    for (int i = 0; i < bound; ++i) {
+      const int j = (i + incur) % n;
+      const double rho_j = j == prev ? rho_prev : c.st->rho[j];
+      const double coef = alpha_of[j] - rho_j * d;
+      const double *s = c.s + (size_t)j * c.n3p;
+      if (i + 1 < bound) {
+        const double *yn = c.y + (size_t)((i + 1 + incur) % n) * c.n3p;
+        double a[1] = {0};
+#pragma unroll
+        for (int e0 = 0; e0 < EPT; e0 += CH) {
+          double sv[CH], yv[CH];
+#pragma unroll
+          for (int u = 0; u < CH; u++) {
+            const int t = tid + (e0 + u) * nth;
+            if (t < n3) sv[u] = s[t], yv[u] = yn[t];
+          }
+#pragma unroll
+          for (int u = 0; u < CH; u++) {
+            const int t = tid + (e0 + u) * nth;
+            if (t < n3) {
+              double rv = fma(coef, sv[u], q[e0 + u]);
+              q[e0 + u] = rv;
+              a[0] = fma(yv[u], rv, a[0]);
+            }
+          }
         }
         tm.reduce<1>(a);
         d = a[0];
       } else {
         double a[2] = {0, 0};
-        for (int t = tm.tid; t < n3; t += tm.nthreads) {
-          double rv = fma(coef, s[t], q[t]);
-          q[t] = rv;
-          a[0] = fma(rv, rv, a[0]);
-          if (w) a[1] = fma(rv, w[t], a[1]);
+        double *out = c.step;
+#pragma unroll
+        for (int e0 = 0; e0 < EPT; e0 += CH) {
+          double sv[CH], wv[CH];
+#pragma unroll
+          for (int u = 0; u < CH; u++) {
+            const int t = tid + (e0 + u) * nth;
+            if (t < n3) {
+              sv[u] = s[t];
+              wv[u] = w ? w[t] : 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < CH; u++) {
+            const int t = tid + (e0 + u) * nth;
+            if (t < n3) {
+              double rv = fma(coef, sv[u], q[e0 + u]);
+              out[t] = rv;
+              a[0] = fma(rv, rv, a[0]);
+              if (w) a[1] = fma(rv, wv[u], a[1]);
+            }
+          }
         }
         tm.reduce<2>(a);
         out_nrm2 = a[0], out_dotw = a[1];
@@ -278,292 +504,15 @@ namespace ofly {
     c.k++;
   }
 
-  struct Work {  // per-team vectors (each n3p doubles)
-    double *x, *g;          // positions; gradient (minimise) or effective gradient (dimer)
+  struct Work {  // per-replica vectors (each n3p doubles)
+    double *base;
+    double *x, *g;  // positions; gradient (minimise) or effective gradient (dimer)
     double *axis, *g0, *g1, *g1p, *dprev, *axisp, *dg;
     Core trans, rot;
   };
 
-  struct Tally {
-    long grad_evals = 0, rebuilds = 0, updates = 0, steps = 0;
-  };
-
-  // Rotor::eff_gradient (rotor.cpp:49-164). Leaves the effective gradient in W.g, the rotated axis in
-  // W.axis and the list positions back where they were. If `step` is non-null the final pass also
-  // returns eff.eff and eff.step. Returns false on Spline::OutOfBounds.
-  template <int C>
-  __device__ __noinline__ bool eff_gradient(Team<C> &tm, const BatchDev &B, const TablesDev &T, const SearchParams &P, Work &W, int r, int n3,
-                               const double *step, double &curv, double &eff2, double &eff_step, Tally &tally) {
-    const double dr = P.delta_r;
-    double4 *pos = B.pos4 + (size_t)r * B.N;
-    W.rot.k = 0;  // m_core.clear()
-
-    if (!team_gradient(tm, B, T, r, W.g0)) return false;
-    tally.grad_evals++;
-    // delta = -dr * axis ; nl.update(delta) ; delta_prev = delta     (rotor.cpp:77-83)
-    for (int i = tm.tid; i < B.N; i += tm.nthreads) {
-      double4 p = ld256(pos + i);
-      double d0 = -dr * W.axis[3 * i], d1 = -dr * W.axis[3 * i + 1], d2 = -dr * W.axis[3 * i + 2];
-      W.dprev[3 * i] = d0, W.dprev[3 * i + 1] = d1, W.dprev[3 * i + 2] = d2;
-      p.x -= d0, p.y -= d1, p.z -= d2;
-      st256(pos + i, p);
-    }
-    tally.updates++;
-    tm.sync();
-    if (!team_gradient(tm, B, T, r, W.g1)) return false;
-    tally.grad_evals++;
-
-    const double inv_n = 1.0 / (double)B.N;
-    for (int it = 0;; it++) {
-      // torque: dg = (g1 - g0) - ((g1 - g0).axis) axis, minus its mean if nothing is frozen (rotor.cpp:89-94)
-      double a7[7] = {0, 0, 0, 0, 0, 0, 0};
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        double dv = W.g1[t] - W.g0[t], av = W.axis[t];
-        a7[0] = fma(dv, av, a7[0]);
-        int c = t % 3;
-        a7[1 + c] += dv, a7[4 + c] += av;
-      }
-      tm.reduce<7>(a7);
-      const double pax = a7[0];
-      double mean[3] = {0, 0, 0};
-      if (P.count_frozen == 0) {
-        for (int c = 0; c < 3; c++) mean[c] = (a7[1 + c] - pax * a7[4 + c]) * inv_n;
-      }
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        W.dg[t] = (W.g1[t] - W.g0[t]) - pax * W.axis[t] - mean[t % 3];
-      }
-      tm.sync();
-
-      double nrm2_unused, th_ax;
-      newton_step(tm, W.rot, W.axis, W.dg, n3, W.axis, nrm2_unused, th_ax);
-      double *theta = W.rot.step;
-      // theta -= (theta.axis) axis ; normalise ; b_1 = (g1-g0).theta / dr   (rotor.cpp:99-103)
-      double a2[2] = {0, 0};
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        double tv = fma(-th_ax, W.axis[t], theta[t]);
-        theta[t] = tv;
-        a2[0] = fma(tv, tv, a2[0]);
-        a2[1] = fma(W.g1[t] - W.g0[t], tv, a2[1]);
-      }
-      tm.reduce<2>(a2);
-      const double inv_th = 1 / sqrt(a2[0]);
-      const double b_1 = a2[1] * inv_th / dr;
-      const double c_x0 = pax / dr;
-      const double theta_1 = -0.5 * atan(b_1 / fabs(c_x0));
-
-      if (fabs(theta_1) < P.rot_theta_tol || (it >= P.iter_max_rot && c_x0 < 0) || it > 10 * P.iter_max_rot) {
-        curv = c_x0;
-        break;
-      }
-      // trial axis, move the list end-point from the old offset to the new one (rotor.cpp:111-116)
-      const double c1 = cos(theta_1), s1 = sin(theta_1);
-      for (int i = tm.tid; i < B.N; i += tm.nthreads) {
-        double4 p = ld256(pos + i);
-        double up[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          int t = 3 * i + c;
-          double tn = theta[t] * inv_th;
-          theta[t] = tn;
-          double ap = W.axis[t] * c1 + tn * s1;
-          W.axisp[t] = ap;
-          double nw = -dr * ap;
-          up[c] = nw - W.dprev[t];
-          W.dprev[t] = nw;
-        }
-        p.x -= up[0], p.y -= up[1], p.z -= up[2];
-        st256(pos + i, p);
-      }
-      tally.updates++;
-      tm.sync();
-      if (!team_gradient(tm, B, T, r, W.g1p)) return false;
-      tally.grad_evals++;
-
-      double a1[1] = {0};
-      for (int t = tm.tid; t < n3; t += tm.nthreads) a1[0] = fma(W.g1p[t] - W.g0[t], W.axisp[t], a1[0]);
-      tm.reduce<1>(a1);
-      const double c_x1 = a1[0] / dr;
-      const double a_1 = (c_x0 - c_x1 + b_1 * sin(2 * theta_1)) / (1 - cos(2 * theta_1));
-      double theta_min = 0.5 * atan(b_1 / a_1);
-      if (a_1 * cos(2 * theta_min) - a_1 + b_1 * sin(2 * theta_min) > 0) theta_min += M_PI / 2;  // extremum was a maximum
-
-      const double cm = cos(theta_min), sm = sin(theta_min);
-      const double k1 = sin(theta_1 - theta_min) / s1, k2 = sm / s1, k3 = 1 - cm - sm * tan(0.5 * theta_1);
-      double ac[1] = {0};
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        double an = W.axis[t] * cm + theta[t] * sm;
-        W.axis[t] = an;
-        double g0v = W.g0[t];
-        double gn = k1 * W.g1[t] + k2 * W.g1p[t] + k3 * g0v;  // interpolated end-point gradient (rotor.cpp:132-134)
-        W.g1[t] = gn;
-        ac[0] = fma(gn - g0v, an, ac[0]);
-      }
-      if (fabs(theta_min) < P.rot_theta_tol) {
-        tm.reduce<1>(ac);
-        curv = ac[0] / dr;
-        break;
-      }
-      tm.sync();
-    }
-
-    // undo the end-point offset (rotor.cpp:150-151) and form the effective gradient (:153-161)
-    double a7[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int t = tm.tid; t < n3; t += tm.nthreads) {
-      double gv = W.g0[t], av = W.axis[t];
-      a7[0] = fma(gv, av, a7[0]);
-      int c = t % 3;
-      a7[1 + c] += gv, a7[4 + c] += av;
-    }
-    tm.reduce<7>(a7);
-    const bool parallel_only = !P.relax_in_convex && curv > 0;
-    const double p0 = a7[0];
-    const double ca = parallel_only ? 0.0 : 1.0, cb = parallel_only ? -p0 : -2 * p0;  // eff = ca g0 + cb axis
-    double mean[3] = {0, 0, 0};
-    if (P.count_frozen == 0) {
-      for (int c = 0; c < 3; c++) mean[c] = (ca * a7[1 + c] + cb * a7[4 + c]) * inv_n;
-    }
-    double a2[2] = {0, 0};
-    for (int i = tm.tid; i < B.N; i += tm.nthreads) {
-      double4 p = ld256(pos + i);
-      p.x += W.dprev[3 * i], p.y += W.dprev[3 * i + 1], p.z += W.dprev[3 * i + 2];
-      st256(pos + i, p);
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        int t = 3 * i + c;
-        double e = ca * W.g0[t] + cb * W.axis[t] - mean[c];
-        W.g[t] = e;
-        a2[0] = fma(e, e, a2[0]);
-        if (step) a2[1] = fma(e, step[t], a2[1]);
-      }
-    }
-    tally.updates++;
-    tm.reduce<2>(a2);
-    eff2 = a2[0], eff_step = a2[1];
-    return true;
-  }
-
-  // Trust-limited step shared by the minimiser and the dimer (lbfgs.cpp:83-100, dimer.cpp:133-151):
-  // Hg *= min(1, trust/|Hg|); acc += |Hg|; x -= Hg; then rebuild if acc > skin/2 else update(Hg).
-  template <int C>
-  __device__ void take_step(Team<C> &tm, const BatchDev &B, const SearchParams &P, Work &W, int r, int n3, double nrm2, double trust,
-                            double &acc, int *scan_smem, Tally &tally) {
-    const double nrm = sqrt(nrm2);
-    const double scale = fmin(1.0, trust / nrm);
-    acc += scale * nrm;
-    const bool rebuild = acc > 0.5 * P.skin;
-    double *step = W.trans.step;
-    double4 *pos = B.pos4 + (size_t)r * B.N;
-    for (int i = tm.tid; i < B.N; i += tm.nthreads) {
-      double h[3];
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        int t = 3 * i + c;
-        h[c] = step[t] * scale;
-        step[t] = h[c];
-        W.x[t] -= h[c];
-      }
-      if (!rebuild) {
-        double4 p = ld256(pos + i);
-        p.x -= h[0], p.y -= h[1], p.z -= h[2];
-        st256(pos + i, p);
-      }
-    }
-    tm.sync();
-    if (rebuild) {
-      team_rebuild(tm, B, r, W.x, scan_smem);
-      acc = 0;
-      tally.rebuilds++;
-    } else {
-      tally.updates++;
-    }
-  }
-
-  __device__ __forceinline__ double next_trust(const SearchParams &P, double trust, double proj) {
-    if (proj < -P.proj_tol) return fmax(P.min_trust, P.shrink_trust * trust);
-    if (proj > P.proj_tol) return fmin(P.max_trust, P.grow_trust * trust);
-    return trust;
-  }
-
-  template <int C>
-  __device__ int run_minimise(Team<C> &tm, const BatchDev &B, const TablesDev &T, const SearchParams &P, Work &W, int r, int n3,
-                              int *scan_smem, Tally &tally) {
-    W.trans.k = 0;
-    team_rebuild(tm, B, r, W.x, scan_smem);
-    tally.rebuilds++;
-    if (__ldcg(B.fault + r) & kFaultCapacity) return kStatusCapacity;
-    if (!team_gradient(tm, B, T, r, W.g)) return kStatusOutOfBounds;
-    tally.grad_evals++;
-    double a2[2] = {0, 0};
-    for (int t = tm.tid; t < n3; t += tm.nthreads) a2[0] = fma(W.g[t], W.g[t], a2[0]);
-    tm.reduce<2>(a2);
-    double mag_g = a2[0];
-    double trust = P.min_trust, acc = 0;
-
-    for (int i = 0; i < P.iter_max; ++i) {
-      if (mag_g < P.f2norm * P.f2norm) return 0;
-      double nrm2, unused;
-      newton_step(tm, W.trans, W.x, W.g, n3, (const double *)nullptr, nrm2, unused);
-      take_step(tm, B, P, W, r, n3, nrm2, trust, acc, scan_smem, tally);
-      if (__ldcg(B.fault + r) & kFaultCapacity) return kStatusCapacity;
-      if (!team_gradient(tm, B, T, r, W.g)) return kStatusOutOfBounds;
-      tally.grad_evals++, tally.steps++;
-      double b2[2] = {0, 0};
-      const double *step = W.trans.step;
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        double gv = W.g[t];
-        b2[0] = fma(gv, gv, b2[0]), b2[1] = fma(gv, step[t], b2[1]);
-      }
-      tm.reduce<2>(b2);
-      mag_g = b2[0];
-      trust = next_trust(P, trust, b2[1]);
-    }
-    return 1;  // iter_max
-  }
-
-  template <int C>
-  __device__ int run_dimer(Team<C> &tm, const BatchDev &B, const TablesDev &T, const SearchParams &P, Work &W, int r, int n3,
-                           int *scan_smem, Tally &tally) {
-    W.trans.k = 0;
-    team_rebuild(tm, B, r, W.x, scan_smem);
-    tally.rebuilds++;
-    if (__ldcg(B.fault + r) & kFaultCapacity) return kStatusCapacity;
-    double curv, mag_g, proj;
-    if (!eff_gradient(tm, B, T, P, W, r, n3, (const double *)nullptr, curv, mag_g, proj, tally)) return kStatusOutOfBounds;
-
-    double trust = P.min_trust, acc = 0, convex_count = 0;
-
-    for (int i = 0; i < P.iter_max; ++i) {
-      if (mag_g < P.f2norm * P.f2norm) return 0;           // success
-      if (convex_count >= P.convex_max) return -1;         // convex
-      if (P.use_history && i % P.hist_check_freq == 0) {   // dimer.cpp:102-131
-        double ctheta = -1;
-        for (long k = 0; k < P.n_sp; k++) {
-          const double *sp = P.hist_sp + (size_t)k * n3;
-          double a3[3] = {0, 0, 0};
-          for (int t = tm.tid; t < n3; t += tm.nthreads) {
-            double m = P.in_min[t];
-            double a = W.x[t] - m, b = sp[t] - m;
-            a3[0] = fma(a, b, a3[0]), a3[1] = fma(b, b, a3[1]), a3[2] = fma(a, a, a3[2]);
-          }
-          tm.reduce<3>(a3);
-          ctheta = fmax(ctheta, a3[0] / (sqrt(a3[1]) * sqrt(a3[2])));
-          if (ctheta > P.cos_theta_tol) return -3;  // collision
-        }
-      }
-      double nrm2, unused;
-      newton_step(tm, W.trans, W.x, W.g, n3, (const double *)nullptr, nrm2, unused);
-      take_step(tm, B, P, W, r, n3, nrm2, trust, acc, scan_smem, tally);
-      if (__ldcg(B.fault + r) & kFaultCapacity) return kStatusCapacity;
-      if (!eff_gradient(tm, B, T, P, W, r, n3, W.trans.step, curv, mag_g, proj, tally)) return kStatusOutOfBounds;
-      tally.steps++;
-      convex_count = curv > 0 ? convex_count + 1 : 0;
-      trust = next_trust(P, trust, proj);
-    }
-    return -2;  // iter_max
-  }
-
-  __device__ __forceinline__ void carve_core(Core &c, double *&p, int n, size_t n3p) {
-    c.n = n, c.k = 0, c.n3p = n3p;
+  __device__ __forceinline__ void carve_core(Core &c, double *&p, int n, size_t n3p, CoreState *st) {
+    c.n = n, c.k = st->k, c.n3p = n3p, c.st = st;
     c.prev_x = p, p += n3p;
     c.prev_g = p, p += n3p;
     c.step = p, p += n3p;
@@ -577,23 +526,35 @@ namespace ofly {
     return v * n3p;
   }
 
-  template <int C>
-  __global__ void __launch_bounds__(kSearchThreads, 1) k_search(BatchDev B, TablesDev T, SearchParams P) {
-    __shared__ double red_smem[team_smem_doubles(C)];
-    __shared__ int scan_smem[33];
-    __shared__ int next_replica;
+  __device__ __forceinline__ double next_trust(const SearchParams &P, double trust, double proj) {
+    if (proj < -P.proj_tol) return fmax(P.min_trust, P.shrink_trust * trust);
+    if (proj > P.proj_tol) return fmin(P.max_trust, P.grow_trust * trust);
+    return trust;
+  }
 
-    Team<C> tm(red_smem);
-    const int team_id = blockIdx.x / C;
-    const int n3 = 3 * B.N;
-    const size_t n3p = ((size_t)n3 + 3) & ~(size_t)3;
-
+  // One replica's segment: everything between two gradient requests. All threads of the team run the
+  // same control flow on identical scalars; thread 0 stores the state that must survive the tick.
+  template <int C, int EPT>
+  struct Segment {
+    Team<C> &tm;
+    const BatchDev &B;
+    const SearchParams &P;
+    const int r, n3;
+    RepState *S;  // global
     Work W;
-    {
-      double *p = P.ws + (size_t)team_id * P.ws_stride;
+    // working copies of the persistent scalars
+    int iter, rot_it, first, need_rebuild;
+    double trust, acc, convex_count, curv, mag_g, c_x0, b_1, theta_1;
+    long tally[4];
+
+    __device__ Segment(Team<C> &tm_, const BatchDev &B_, const SearchParams &P_, int r_) : tm(tm_), B(B_), P(P_), r(r_), n3(3 * B_.N) {
+      S = P.state + r;
+      const size_t n3p = ((size_t)n3 + 3) & ~(size_t)3;
+      double *p = P.ws + (size_t)r * P.ws_stride;
+      W.base = p;
       W.x = p, p += n3p;
       W.g = p, p += n3p;
-      carve_core(W.trans, p, P.n_hist, n3p);
+      carve_core(W.trans, p, P.n_hist, n3p, &S->trans);
       if (P.mode == 1) {
         W.axis = p, p += n3p;
         W.g0 = p, p += n3p;
@@ -602,37 +563,44 @@ namespace ofly {
         W.dprev = p, p += n3p;
         W.axisp = p, p += n3p;
         W.dg = p, p += n3p;
-        carve_core(W.rot, p, P.rot_n, n3p);
+        carve_core(W.rot, p, P.rot_n, n3p, &S->rot);
+      }
+      iter = S->iter, rot_it = S->rot_it, first = S->first, need_rebuild = 0;
+      trust = S->trust, acc = S->acc, convex_count = S->convex_count, curv = S->curv, mag_g = S->mag_g;
+      c_x0 = S->c_x0, b_1 = S->b_1, theta_1 = S->theta_1;
+      for (int q = 0; q < 4; q++) tally[q] = S->tally[q];
+    }
+
+    __device__ double4 *pos() const { return B.pos4 + (size_t)r * B.N; }
+    // Component t = 3 i + c of a [3N] vector lives at double index 4 i + c of the replica's pos4 records.
+    // Every pass, including the list-position updates, is indexed by t, so a thread only ever re-reads
+    // what it wrote itself: inside a segment no global data crosses threads.
+    static __device__ __forceinline__ int pos_slot(int t) { return t + t / 3; }
+
+    __device__ __forceinline__ void lbfgs_step(Core &c, const double *x, const double *g, const double *w, double &nrm2, double &dotw) {
+      if constexpr (EPT > 0) {
+        newton_step_reg<C, EPT>(tm, c, x, g, n3, w, nrm2, dotw);
+      } else {
+        newton_step(tm, c, x, g, n3, w, nrm2, dotw);
       }
     }
 
-    for (;;) {
-      // the team leader claims the next replica; every CTA of the cluster learns it through its own smem
+    // Suspend until the gradient of the current list positions is in `dst`; resume at `phase`.
+    __device__ void yield(int phase, double *dst) {
       if (tm.tid == 0) {
-        int r = atomicAdd(P.queue, 1);
-        if constexpr (C > 1) {
-          cg::cluster_group cl = cg::this_cluster();
-          for (int c = 0; c < C; c++) *cl.map_shared_rank(&next_replica, c) = r;
-        } else {
-          next_replica = r;
-        }
+        S->phase = phase, S->iter = iter, S->rot_it = rot_it, S->first = first, S->need_rebuild = need_rebuild;
+        S->gdst = (unsigned long long)(dst - W.base);
+        S->trust = trust, S->acc = acc, S->convex_count = convex_count, S->curv = curv, S->mag_g = mag_g;
+        S->c_x0 = c_x0, S->b_1 = b_1, S->theta_1 = theta_1;
+        S->trans.k = W.trans.k;
+        if (P.mode == 1) S->rot.k = W.rot.k;
+        for (int q = 0; q < 4; q++) S->tally[q] = tally[q];
       }
-      tm.sync();
-      const int r = next_replica;
-      tm.sync();
-      if (r >= B.R) break;
+    }
 
-      for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        W.x[t] = P.pos_in[(size_t)r * n3 + t];
-        if (P.mode == 1) W.axis[t] = P.axis_in[(size_t)r * n3 + t];
-      }
-      if (tm.tid == 0) B.fault[r] = 0;
-      tm.sync();
-
-      Tally tally;
-      int status = P.mode == 0 ? run_minimise(tm, B, T, P, W, r, n3, scan_smem, tally) : run_dimer(tm, B, T, P, W, r, n3, scan_smem, tally);
-
-      tm.sync();
+    // Write the results of a finished replica.
+    __device__ void finish(int status) {
+      __syncthreads();
       for (int t = tm.tid; t < n3; t += tm.nthreads) {
         P.pos_out[(size_t)r * n3 + t] = W.x[t];
         if (P.mode == 1) P.axis_out[(size_t)r * n3 + t] = W.axis[t];
@@ -642,10 +610,369 @@ namespace ofly {
         P.status[r] = status;
         if (P.counters) {
           long *c = P.counters + 4 * (size_t)r;
-          c[0] = tally.grad_evals, c[1] = tally.rebuilds, c[2] = tally.updates, c[3] = tally.steps;
+          for (int q = 0; q < 4; q++) c[q] = tally[q];
+        }
+        S->phase = kDone, S->status = status, S->need_rebuild = 0;
+      }
+    }
+
+    // neigh::List::rebuild(x) request: the grid kernels of this tick do the work; the histogram of
+    // the replica must be zero before they start.
+    __device__ void request_rebuild() {
+      int *hist = B.cell_count + (size_t)r * B.grid.ncells;
+      for (int c = tm.tid; c < B.grid.ncells; c += tm.nthreads) hist[c] = 0;
+      need_rebuild = 1;
+      tally[1]++;
+    }
+
+    // Trust-limited step shared by the minimiser and the dimer (lbfgs.cpp:83-100, dimer.cpp:133-151):
+    // Hg *= min(1, trust/|Hg|); acc += |Hg|; x -= Hg; then rebuild if acc > skin/2 else update(Hg).
+    __device__ void take_step(double nrm2) {
+      const double nrm = sqrt(nrm2);
+      const double scale = fmin(1.0, trust / nrm);
+      acc += scale * nrm;
+      const bool rebuild = acc > 0.5 * P.skin;
+      double *step = W.trans.step;
+      double *p4 = reinterpret_cast<double *>(pos());
+      {
+        const double *const src[2] = {step, W.x};
+        team_pass<2>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[2]) {
+          const double h = v[0] * scale;
+          step[t] = h;
+          W.x[t] = v[1] - h;
+          if (!rebuild) p4[pos_slot(t)] -= h;
+        });
+      }
+      if (rebuild) {
+        request_rebuild();
+        acc = 0;
+      } else {
+        tally[2]++;
+      }
+    }
+
+    // ---- minimise::LBFGS::minimise ----------------------------------------------------------------
+    __device__ void run_minimise(int phase) {
+      if (phase == kInit) {
+        for (int t = tm.tid; t < n3; t += tm.nthreads) W.x[t] = P.pos_in[(size_t)r * n3 + t];
+        W.trans.k = 0;
+        iter = 0, first = 1, trust = P.min_trust, acc = 0;
+        for (int q = 0; q < 4; q++) tally[q] = 0;
+        request_rebuild();
+        return yield(kMinGrad, W.g);
+      }
+      // phase == kMinGrad: the gradient at x is in W.g
+      tally[0]++;
+      double b2[2] = {0, 0};
+      const double *step = W.trans.step;
+      {
+        const double *const src[2] = {W.g, step};
+        const bool with_step = !first;
+        team_pass<2>(tm.tid, tm.nthreads, n3, src, [&](int, const double(&v)[2]) {
+          b2[0] = fma(v[0], v[0], b2[0]);
+          if (with_step) b2[1] = fma(v[0], v[1], b2[1]);
+        });
+      }
+      tm.reduce<2>(b2);
+      mag_g = b2[0];
+      if (!first) {
+        tally[3]++;
+        trust = next_trust(P, trust, b2[1]);
+        iter++;
+      }
+      first = 0;
+      if (iter >= P.iter_max) return finish(1);                 // iter_max
+      if (mag_g < P.f2norm * P.f2norm) return finish(0);        // converged
+      double nrm2, unused;
+      lbfgs_step(W.trans, W.x, W.g, (const double *)nullptr, nrm2, unused);
+      take_step(nrm2);
+      yield(kMinGrad, W.g);
+    }
+
+    // ---- saddle::Rotor::eff_gradient + saddle::Dimer::find_sp ---------------------------------------
+    // Returns true if the replica finished or suspended; false never.
+    __device__ void run_dimer(int phase) {
+      const double dr = P.delta_r;
+      const double inv_n = 1.0 / (double)B.N;
+      double *p4 = reinterpret_cast<double *>(pos());
+
+      if (phase == kInit) {
+        for (int t = tm.tid; t < n3; t += tm.nthreads) {
+          W.x[t] = P.pos_in[(size_t)r * n3 + t];
+          W.axis[t] = P.axis_in[(size_t)r * n3 + t];
+        }
+        W.trans.k = 0, W.rot.k = 0;
+        iter = 0, first = 1, trust = P.min_trust, acc = 0, convex_count = 0;
+        for (int q = 0; q < 4; q++) tally[q] = 0;
+        request_rebuild();
+        return yield(kRotG0, W.g0);  // eff_gradient starts with pot.gradient(g0) (rotor.cpp:75)
+      }
+
+      bool rot_head = false;
+      if (phase == kRotG0) {
+        // delta = -dr * axis ; nl.update(delta) ; delta_prev = delta ; gradient(g1)   (rotor.cpp:77-85)
+        tally[0]++;
+        W.rot.k = 0;  // m_core.clear()
+        for (int t = tm.tid; t < n3; t += tm.nthreads) {
+          const double d = -dr * W.axis[t];
+          W.dprev[t] = d;
+          p4[pos_slot(t)] -= d;
+        }
+        tally[2]++;
+        return yield(kRotG1, W.g1);
+      }
+      if (phase == kRotG1) {
+        tally[0]++;
+        rot_it = 0;
+        rot_head = true;
+      }
+      if (phase == kRotG1p) {
+        // the trial gradient g1p at axis' arrived (rotor.cpp:118-134)
+        tally[0]++;
+        const double *theta = W.rot.step;
+        double a1[1] = {0};
+        {
+          const double *const src[3] = {W.g1p, W.g0, W.axisp};
+          team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int, const double(&v)[3]) { a1[0] = fma(v[0] - v[1], v[2], a1[0]); });
+        }
+        tm.reduce<1>(a1);
+        const double s1 = sin(theta_1);
+        const double c_x1 = a1[0] / dr;
+        const double a_1 = (c_x0 - c_x1 + b_1 * sin(2 * theta_1)) / (1 - cos(2 * theta_1));
+        double theta_min = 0.5 * atan(b_1 / a_1);
+        if (a_1 * cos(2 * theta_min) - a_1 + b_1 * sin(2 * theta_min) > 0) theta_min += M_PI / 2;  // extremum was a maximum
+
+        const double cm = cos(theta_min), sm = sin(theta_min);
+        const double k1 = sin(theta_1 - theta_min) / s1, k2 = sm / s1, k3 = 1 - cm - sm * tan(0.5 * theta_1);
+        double ac[1] = {0};
+        {
+          const double *const src[5] = {W.axis, theta, W.g0, W.g1, W.g1p};
+          team_pass<5>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[5]) {
+            double an = v[0] * cm + v[1] * sm;
+            W.axis[t] = an;
+            double g0v = v[2];
+            double gn = k1 * v[3] + k2 * v[4] + k3 * g0v;  // interpolated end-point gradient (rotor.cpp:132-134)
+            W.g1[t] = gn;
+            ac[0] = fma(gn - g0v, an, ac[0]);
+          });
+        }
+        if (fabs(theta_min) < P.rot_theta_tol) {
+          tm.reduce<1>(ac);
+          curv = ac[0] / dr;
+        } else {
+          __syncthreads();
+          rot_it++;
+          rot_head = true;
         }
       }
-      tm.sync();
+
+      if (rot_head) {
+        // torque: dg = (g1 - g0) - ((g1 - g0).axis) axis, minus its mean if nothing is frozen (rotor.cpp:89-94)
+        double a7[7] = {0, 0, 0, 0, 0, 0, 0};
+        {
+          const double *const src[3] = {W.g1, W.g0, W.axis};
+          team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
+            double dv = v[0] - v[1], av = v[2];
+            a7[0] = fma(dv, av, a7[0]);
+            int c = t % 3;
+            a7[1 + c] += dv, a7[4 + c] += av;
+          });
+        }
+        tm.reduce<7>(a7);
+        const double pax = a7[0];
+        double mean[3] = {0, 0, 0};
+        if (P.count_frozen == 0) {
+          for (int c = 0; c < 3; c++) mean[c] = (a7[1 + c] - pax * a7[4 + c]) * inv_n;
+        }
+        {
+          const double *const src[3] = {W.g1, W.g0, W.axis};
+          team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) { W.dg[t] = (v[0] - v[1]) - pax * v[2] - mean[t % 3]; });
+        }
+        __syncthreads();
+
+        double nrm2_unused, th_ax;
+        lbfgs_step(W.rot, W.axis, W.dg, W.axis, nrm2_unused, th_ax);
+        double *theta = W.rot.step;
+        // theta -= (theta.axis) axis ; normalise ; b_1 = (g1-g0).theta / dr   (rotor.cpp:99-103)
+        double a2[2] = {0, 0};
+        {
+          const double *const src[4] = {W.axis, theta, W.g1, W.g0};
+          team_pass<4>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[4]) {
+            double tv = fma(-th_ax, v[0], v[1]);
+            theta[t] = tv;
+            a2[0] = fma(tv, tv, a2[0]);
+            a2[1] = fma(v[2] - v[3], tv, a2[1]);
+          });
+        }
+        tm.reduce<2>(a2);
+        const double inv_th = 1 / sqrt(a2[0]);
+        b_1 = a2[1] * inv_th / dr;
+        c_x0 = pax / dr;
+        theta_1 = -0.5 * atan(b_1 / fabs(c_x0));
+
+        if (fabs(theta_1) < P.rot_theta_tol || (rot_it >= P.iter_max_rot && c_x0 < 0) || rot_it > 10 * P.iter_max_rot) {
+          curv = c_x0;
+        } else {
+          // trial axis, move the list end-point from the old offset to the new one (rotor.cpp:111-116)
+          const double c1 = cos(theta_1), s1 = sin(theta_1);
+          {
+            const double *const src[3] = {theta, W.axis, W.dprev};
+            team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
+              const double tn = v[0] * inv_th;
+              theta[t] = tn;
+              const double ap = v[1] * c1 + tn * s1;
+              W.axisp[t] = ap;
+              const double nw = -dr * ap;
+              W.dprev[t] = nw;
+              p4[pos_slot(t)] -= nw - v[2];
+            });
+          }
+          tally[2]++;
+          return yield(kRotG1p, W.g1p);
+        }
+      }
+
+      // ---- rotation finished: undo the end-point offset (rotor.cpp:150-151), effective gradient (:153-161)
+      {
+        double a7[7] = {0, 0, 0, 0, 0, 0, 0};
+        {
+          const double *const src[2] = {W.g0, W.axis};
+          team_pass<2>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[2]) {
+            a7[0] = fma(v[0], v[1], a7[0]);
+            int c = t % 3;
+            a7[1 + c] += v[0], a7[4 + c] += v[1];
+          });
+        }
+        tm.reduce<7>(a7);
+        const bool parallel_only = !P.relax_in_convex && curv > 0;
+        const double p0 = a7[0];
+        const double ca = parallel_only ? 0.0 : 1.0, cb = parallel_only ? -p0 : -2 * p0;  // eff = ca g0 + cb axis
+        double mean[3] = {0, 0, 0};
+        if (P.count_frozen == 0) {
+          for (int c = 0; c < 3; c++) mean[c] = (ca * a7[1 + c] + cb * a7[4 + c]) * inv_n;
+        }
+        const double *step = W.trans.step;
+        double a2[2] = {0, 0};
+        {
+          const double *const src[4] = {W.g0, W.axis, W.dprev, step};
+          const bool with_step = !first;
+          team_pass<4>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[4]) {
+            p4[pos_slot(t)] += v[2];
+            const double e = ca * v[0] + cb * v[1] - mean[t % 3];
+            W.g[t] = e;
+            a2[0] = fma(e, e, a2[0]);
+            if (with_step) a2[1] = fma(e, v[3], a2[1]);
+          });
+        }
+        tally[2]++;
+        tm.reduce<2>(a2);
+        mag_g = a2[0];
+        if (!first) {  // tail of the translation loop body (dimer.cpp:153-167)
+          tally[3]++;
+          convex_count = curv > 0 ? convex_count + 1 : 0;
+          trust = next_trust(P, trust, a2[1]);
+          iter++;
+        }
+        first = 0;
+      }
+
+      // ---- head of the translation loop (dimer.cpp:73-151)
+      if (iter >= P.iter_max) return finish(-2);                   // iter_max
+      if (mag_g < P.f2norm * P.f2norm) return finish(0);           // success
+      if (convex_count >= P.convex_max) return finish(-1);         // convex
+      if (P.use_history && iter % P.hist_check_freq == 0) {        // dimer.cpp:102-131
+        double ctheta = -1;
+        for (long k = 0; k < P.n_sp; k++) {
+          const double *sp = P.hist_sp + (size_t)k * n3;
+          double a3[3] = {0, 0, 0};
+          const double *const src[3] = {P.in_min, W.x, sp};
+          team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int, const double(&v)[3]) {
+            double a = v[1] - v[0], b = v[2] - v[0];
+            a3[0] = fma(a, b, a3[0]), a3[1] = fma(b, b, a3[1]), a3[2] = fma(a, a, a3[2]);
+          });
+          tm.reduce<3>(a3);
+          ctheta = fmax(ctheta, a3[0] / (sqrt(a3[1]) * sqrt(a3[2])));
+          if (ctheta > P.cos_theta_tol) return finish(-3);  // collision
+        }
+      }
+      double nrm2, unused;
+      lbfgs_step(W.trans, W.x, W.g, (const double *)nullptr, nrm2, unused);
+      take_step(nrm2);
+      yield(kRotG0, W.g0);
+    }
+  };
+
+  // One tick's vector algebra: gridDim.x = R * C, team t owns replica t.
+  // MAXT = 512: large systems, up to 128 registers so the batched loads of team_pass stay in registers;
+  // MAXT = 128: small systems with thousands of replicas, 8 teams resident per SM.
+  // EPT > 0: n3 <= EPT * team threads, L-BFGS runs with q in registers; EPT = 0: any size.
+  template <int C, int MAXT, int EPT>
+  __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 4 : 1) k_segment(BatchDev B, SearchParams P) {
+    __shared__ double red_smem[team_smem_doubles(C)];
+    __shared__ uint64_t red_bar[2];
+    __shared__ int last_team;
+
+    Team<C> tm(red_smem, red_bar);
+    const int r = blockIdx.x / C;
+    const int n_teams = gridDim.x / C;
+
+    const int phase = P.state[r].phase;
+    if (phase != kDone) {
+      tm.init();
+      const int fault = __ldcg(B.fault + r);
+      Segment<C, EPT> seg(tm, B, P, r);
+      if (phase != kInit && (fault & kFaultCapacity)) {
+        seg.finish(kStatusCapacity);
+      } else if (phase != kInit && (fault & kFaultOutOfBounds)) {
+        seg.finish(kStatusOutOfBounds);  // the reference throws Spline::OutOfBounds out of find_sp / minimise
+      } else if (P.state[r].iter < 0) {
+        seg.finish(kStatusUnfinished);
+      } else {
+        if (phase == kInit && tm.tid == 0) B.fault[r] = 0;
+        if (P.mode == 0) {
+          seg.run_minimise(phase);
+        } else {
+          seg.run_dimer(phase);
+        }
+      }
+      tm.fini();
+    }
+
+    // The last team to arrive compiles the selection lists of this tick (in replica order, so the
+    // grid kernels see a deterministic work order) and decides whether the graph body repeats.
+    if (tm.rank == 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        last_team = atomicAdd(&P.ctl->ticket, 1) == n_teams - 1;
+      }
+      __syncthreads();
+      if (last_team && threadIdx.x < 32) {
+        __threadfence();
+        const int lane = threadIdx.x;
+        const int tick = P.ctl->tick + 1;
+        const bool out_of_ticks = tick >= P.max_ticks;
+        int na = 0, nr = 0;
+        for (int base = 0; base < B.R; base += 32) {
+          int q = base + lane;
+          bool act = false, reb = false;
+          if (q < B.R) {
+            volatile RepState *s = P.state + q;
+            act = s->phase != kDone;
+            reb = act && s->need_rebuild != 0;
+            if (act && out_of_ticks) s->iter = -1;  // flagged: finishes as kStatusUnfinished next tick
+          }
+          unsigned ma = __ballot_sync(0xffffffffu, act), mr = __ballot_sync(0xffffffffu, reb);
+          if (act) P.active[na + __popc(ma & ((1u << lane) - 1u))] = q;
+          if (reb) P.rebuild[nr + __popc(mr & ((1u << lane) - 1u))] = q;
+          na += __popc(ma), nr += __popc(mr);
+        }
+        if (lane == 0) {
+          P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;
+          __threadfence();
+          if (P.use_cond) cudaGraphSetConditional(P.cond, (na > 0 && tick <= P.max_ticks) ? 1u : 0u);
+        }
+      }
     }
   }
 

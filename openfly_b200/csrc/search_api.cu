@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <string>
 
 #include "internal.hpp"
 #include "search.cuh"
@@ -11,6 +12,7 @@ namespace ofly {
   int collect_faults(ofly_batch *b);
   void make_grid_for(ofly_batch *b, double r_list);
   void grow_buffers(ofly_batch *b);
+  int pick_group(ofly_ctx *ctx, long atoms);
 
   namespace {
 
@@ -31,23 +33,39 @@ namespace ofly {
       if (!ok) throw Error(OFLY_ERR_INVALID, msg);
     }
 
-    // Cluster width: as many SMs per replica as the batch leaves free, but never more CTAs than the
-    // replica has rounds of atoms for.
-    int pick_cluster(ofly_ctx *ctx, long R, long N) {
-      if (char const *v = std::getenv("OFLY_CLUSTER")) {
-        int c = std::atoi(v);
-        if (c == 1 || c == 2 || c == 4 || c == 8) return c;
-      }
-      int c = 1;
-      while (c < 8 && R * (c * 2) <= ctx->sm_count && (long)(c * 2) * kSearchThreads / kSearchGroup <= N) c *= 2;
-      return c;
+    constexpr int kSegMaxThreads = 512;
+    constexpr int kSegEpt = 16;         // elements per thread the register-resident L-BFGS step can hold
+    constexpr int kTickNodes = 8;       // kernels per tick
+    constexpr int kHostLoopTicks = 8;   // ticks between host checks when the device-side loop is off
+
+    int env_int(char const *name, int dflt) {
+      char const *v = std::getenv(name);
+      return v ? std::atoi(v) : dflt;
     }
 
-    template <int C>
-    void launch_search(ofly_ctx *ctx, int teams, BatchDev const &B, TablesDev const &T, SearchParams const &P) {
+    struct TeamShape {
+      int threads, cluster;
+    };
+
+    // Team of one replica's vector algebra: >= 16 elements per thread before the CTA is widened, then a
+    // cluster while every thread keeps >= 8 elements. The passes are latency-bound streams, and late in a
+    // batch only a few replicas are still active, so wide teams are what keeps bytes in flight.
+    TeamShape pick_team(ofly_ctx *, long, long n3) {
+      TeamShape t{128, 1};
+      while (t.threads < kSegMaxThreads && n3 > (long)t.threads * 16) t.threads *= 2;
+      if (t.threads == kSegMaxThreads) {
+        while (t.cluster < 8 && n3 > (long)t.cluster * t.threads * 8) t.cluster *= 2;
+      }
+      int forced = env_int("OFLY_CLUSTER", 0);
+      if (forced == 1 || forced == 2 || forced == 4 || forced == 8) t.cluster = forced;
+      return t;
+    }
+
+    template <int C, int MAXT, int EPT>
+    void launch_segment(ofly_ctx *ctx, int teams, int threads, BatchDev const &B, SearchParams const &P) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(teams * C));
-      cfg.blockDim = dim3(kSearchThreads);
+      cfg.blockDim = dim3((unsigned)threads);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = ctx->stream;
       cudaLaunchAttribute attr[1];
@@ -55,8 +73,134 @@ namespace ofly {
       attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = C > 1 ? 1 : 0;
-      OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_search<C>, B, T, P));
-      ctx->launches++;
+      OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT, EPT>, B, P));
+    }
+
+    unsigned stride_grid(ofly_ctx *ctx, size_t items, int per_sm) {
+      return (unsigned)std::max<size_t>(1, std::min<size_t>(items, (size_t)ctx->sm_count * per_sm));
+    }
+
+    // One tick: segment, rebuild of the flagged replicas, gradient of the active ones (search.cuh).
+    void enqueue_tick(ofly_batch *b, SearchParams const &P, TeamShape shape) {
+      ofly_ctx *ctx = b->ctx;
+      cudaStream_t st = ctx->stream;
+      BatchDev const &B = b->d;
+      TablesDev const &T = b->tables->dev;
+      const size_t atoms = (size_t)b->R * b->N;
+      const bool in_regs = 3 * b->N <= (long)kSegEpt * shape.threads * shape.cluster;
+      const int teams = (int)b->R;
+#define OFLY_SEG(C, T)                                                   \
+  if (in_regs) {                                                         \
+    launch_segment<C, T, kSegEpt>(ctx, teams, shape.threads, B, P);      \
+  } else {                                                               \
+    launch_segment<C, T, 0>(ctx, teams, shape.threads, B, P);            \
+  }
+      switch (shape.cluster) {
+        case 8:
+          OFLY_SEG(8, kSegMaxThreads);
+          break;
+        case 4:
+          OFLY_SEG(4, kSegMaxThreads);
+          break;
+        case 2:
+          OFLY_SEG(2, kSegMaxThreads);
+          break;
+        default:
+          if (shape.threads <= 128) {
+            OFLY_SEG(1, 128);
+          } else {
+            OFLY_SEG(1, kSegMaxThreads);
+          }
+          break;
+      }
+#undef OFLY_SEG
+      Sel reb{P.rebuild, &P.ctl->n_rebuild}, act{P.active, &P.ctl->n_active};
+      k_nb_canon_count<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb, P.ws, P.ws_stride);
+      k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(B, reb);
+      k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb);
+      k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
+      const unsigned long long *goff = &P.state->gdst;
+      const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
+      const int G = pick_group(ctx, (long)atoms);
+      const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
+      const unsigned gg = stride_grid(ctx, tiles, 8);
+      switch (G) {
+        case 32:
+          k_nb_build<32><<<gg, 256, 0, st>>>(B, reb);
+          k_eam_rho<32><<<gg, 256, 0, st>>>(B, T, act);
+          k_eam_force<32><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        case 16:
+          k_nb_build<16><<<gg, 256, 0, st>>>(B, reb);
+          k_eam_rho<16><<<gg, 256, 0, st>>>(B, T, act);
+          k_eam_force<16><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        case 8:
+          k_nb_build<8><<<gg, 256, 0, st>>>(B, reb);
+          k_eam_rho<8><<<gg, 256, 0, st>>>(B, T, act);
+          k_eam_force<8><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        default:
+          k_nb_build<4><<<gg, 256, 0, st>>>(B, reb);
+          k_eam_rho<4><<<gg, 256, 0, st>>>(B, T, act);
+          k_eam_force<4><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+      }
+      OFLY_CUDA(cudaGetLastError());
+    }
+
+    struct GraphGuard {
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      ~GraphGuard() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+      }
+    };
+
+    // The whole search as ONE graph launch: a WHILE conditional node whose body is one tick; the
+    // segment kernel clears the condition when no replica is active.
+    void run_device_loop(ofly_batch *b, SearchParams P, TeamShape shape) {
+      ofly_ctx *ctx = b->ctx;
+      GraphGuard g;
+      OFLY_CUDA(cudaGraphCreate(&g.graph, 0));
+      cudaGraphConditionalHandle handle;
+      OFLY_CUDA(cudaGraphConditionalHandleCreate(&handle, g.graph, 1, cudaGraphCondAssignDefault));
+      cudaGraphNodeParams np{};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = handle;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      OFLY_CUDA(cudaGraphAddNode(&node, g.graph, nullptr, 0, &np));
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      P.use_cond = 1, P.cond = handle;
+      OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue_tick(b, P, shape);
+      } catch (...) {
+        cudaGraph_t dead = nullptr;
+        cudaStreamEndCapture(ctx->stream, &dead);
+        throw;
+      }
+      OFLY_CUDA(cudaStreamEndCapture(ctx->stream, nullptr));
+      OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+      OFLY_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+      OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    // Fallback / profiling mode (OFLY_SEARCH_LOOP=host): plain launches, the host looks at the active
+    // count every kHostLoopTicks ticks.
+    void run_host_loop(ofly_batch *b, SearchParams P, TeamShape shape) {
+      ofly_ctx *ctx = b->ctx;
+      P.use_cond = 0;
+      Control c{};
+      for (;;) {
+        for (int t = 0; t < kHostLoopTicks; t++) enqueue_tick(b, P, shape);
+        OFLY_CUDA(cudaMemcpyAsync(&c, P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+        OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (c.n_active == 0 || c.tick > P.max_ticks + 1) break;
+      }
     }
 
     struct DevPtrs {
@@ -72,6 +216,7 @@ namespace ofly {
       OFLY_CUDA(cudaSetDevice(ctx->device));
       require(P.n_hist >= 1 && P.n_hist <= kMaxHist, "L-BFGS history size must be in [1, 16]");
       require(P.mode == 0 || (P.rot_n >= 1 && P.rot_n <= kMaxHist), "rotor L-BFGS history size must be in [1, 16]");
+      require(P.iter_max >= 0, "iteration limit is negative");
 
       // skin = max(skin_frac^(1/3) - 1, 0) * r   (lbfgs.cpp:39, dimer.cpp:47)
       double skin = std::max(std::pow(skin_frac, 1. / 3.) - 1, 0.0) * base_radius;
@@ -79,35 +224,47 @@ namespace ofly {
       P.skin = skin;
       if (!(b->r_list == r_list)) make_grid_for(b, r_list);
 
+      const size_t R = (size_t)b->R;
       const size_t n3p = ((size_t)3 * b->N + 3) & ~(size_t)3;
-      const int C = pick_cluster(ctx, b->R, b->N);
-      const int teams = (int)std::min<long>(b->R, std::max(1, ctx->sm_count / C));
+      const TeamShape shape = pick_team(ctx, b->R, 3 * b->N);
       P.ws_stride = search_ws_doubles(P.mode, P.n_hist, P.rot_n, n3p);
-      b->search_ws.reserve((P.ws_stride * (size_t)teams) * sizeof(double) + 256);
-      P.ws = reinterpret_cast<double *>(b->search_ws.p + 256);
-      P.queue = reinterpret_cast<int *>(b->search_ws.p);
+
+      // arena: control block | replica states | two selection lists | vectors
+      static_assert(sizeof(RepState) % 8 == 0 && sizeof(Control) % 8 == 0, "layout");
+      const size_t head = 256 + ((R * sizeof(RepState) + 2 * R * sizeof(int) + 255) & ~(size_t)255);
+      b->search_ws.reserve(head + P.ws_stride * R * sizeof(double));
+      char *base = b->search_ws.p;
+      P.ctl = reinterpret_cast<Control *>(base);
+      P.state = reinterpret_cast<RepState *>(base + 256);
+      P.active = reinterpret_cast<int *>(base + 256 + R * sizeof(RepState));
+      P.rebuild = P.active + R;
+      P.ws = reinterpret_cast<double *>(base + head);
       P.pos_in = io.pos_in, P.axis_in = io.axis_in, P.in_min = io.in_min, P.hist_sp = io.hist_sp;
       P.pos_out = io.pos_out, P.axis_out = io.axis_out, P.grad_out = io.grad_out, P.status = io.status, P.counters = io.counters;
+      // gradient requests per replica are bounded by steps x (2 + rotations); the budget only guards
+      // against a device-side loop that would otherwise never end.
+      const long per_step = P.mode == 0 ? 1 : 2 + 10L * std::max(1, P.iter_max_rot) + 2;
+      P.max_ticks = (int)std::min<long>((long)(P.iter_max + 1) * per_step + 8, 1L << 30);
+
+      const bool device_loop = [] {
+        char const *v = std::getenv("OFLY_SEARCH_LOOP");
+        return !(v && std::string(v) == "host");
+      }();
 
       for (int attempt = 0;; attempt++) {
-        OFLY_CUDA(cudaMemsetAsync(P.queue, 0, sizeof(int), ctx->stream));
-        switch (C) {
-          case 8:
-            launch_search<8>(ctx, teams, b->d, b->tables->dev, P);
-            break;
-          case 4:
-            launch_search<4>(ctx, teams, b->d, b->tables->dev, P);
-            break;
-          case 2:
-            launch_search<2>(ctx, teams, b->d, b->tables->dev, P);
-            break;
-          default:
-            launch_search<1>(ctx, teams, b->d, b->tables->dev, P);
-            break;
+        OFLY_CUDA(cudaMemsetAsync(base, 0, head, ctx->stream));
+        if (device_loop) {
+          run_device_loop(b, P, shape);
+        } else {
+          run_host_loop(b, P, shape);
         }
+        Control c{};
+        OFLY_CUDA(cudaMemcpyAsync(&c, P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
         b->built = true;
-        // The fault words double as the capacity report; reading them is the call's one synchronisation.
+        // The fault words double as the capacity report; reading them is the call's synchronisation.
         int f = collect_faults(b);
+        ctx->launches += (long)c.tick * kTickNodes;  // kernels executed (by the device-side loop or the host loop)
+        if (c.n_active != 0) throw Error(OFLY_ERR_CUDA, "search loop ended with active replicas");
         if (!(f & kFaultCapacity)) break;
         if (attempt == 2) throw Error(OFLY_ERR_CAPACITY, "neighbour buffers overflowed after regrowing");
         grow_buffers(b);

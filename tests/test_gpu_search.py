@@ -1,0 +1,201 @@
+"""GPU parity: minimise::LBFGS::minimise and saddle::Dimer::find_sp (lock-step engine, through the C ABI)
+against the CPU oracle on identical start states.
+
+The reference has no tests for saddle/ or minimise/ (SURVEY.md 4), so these trajectories are pinned
+oracle-vs-GPU only: same exit codes, saddle positions, barriers to 1e-6 eV (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import WEN, bcc_vacancy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from openfly_b200 import fly
+
+    ctx = fly.Context(0)
+    data = fly.DataEAM(ctx, WEN)
+    yield fly, ctx, data
+    data.close()
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def otab(oracle_lib):
+    return oracle_lib.Tables(WEN)
+
+
+@pytest.fixture(scope="module")
+def small_cell(gpu, otab, oracle_lib):
+    """4^3 bcc Fe - 1 vacancy + 1 H (128 atoms), relaxed by the oracle; 8 Master::perturb start states."""
+    base, ex, ids = bcc_vacancy(4, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    osys = oracle_lib.System(otab, ex)
+    r0, g0, failed, cnt = osys.minimise(base, ids, fz, threads=4)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(8)]
+    P = np.stack([s[0] for s in starts])
+    A = np.stack([s[1] for s in starts])
+    return base, ex, ids, fz, osys, r0, P, A
+
+
+def _energy(osys, otab, ids, r):
+    osys.rebuild(otab.rcut, r)
+    return osys.energy(ids, 4)
+
+
+def test_minimise_matches_oracle(gpu, otab, small_cell):
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    r1, g1, failed, cnt = fly.LBFGS().minimise(s, base, fly.Generic(data))
+    assert not failed[0]
+    assert np.abs(r1[0] - r0).max() < 1e-6
+    assert np.sqrt((g1[0] ** 2).sum()) < 1e-6  # f2norm
+    E0, E1 = _energy(osys, otab, ids, r0), _energy(osys, otab, ids, r1[0])
+    assert abs(E1 - E0) < 1e-9
+    assert cnt[0, 0] >= 2 and cnt[0, 1] >= 1
+    s.close()
+
+
+def test_minimise_batch_iter_max_and_frozen(gpu, otab, oracle_lib, small_cell):
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    fz2 = fz.copy()
+    fz2[3] = 1
+    R = 3
+    pos = np.stack([oracle_lib.jitter(base, (9, 2, 3, 4 + r), 0.05) for r in range(R)])
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz2, replicas=R)
+    out_r, out_g, failed, cnt = fly.LBFGS().minimise(s, pos, fly.Generic(data))
+    o_r, o_g, o_fail, o_cnt = osys.minimise_batch(pos, ids, fz2, threads=3)
+    assert failed.tolist() == [bool(x) for x in o_fail]
+    assert np.abs(out_r - o_r).max() < 1e-6
+    assert np.all(out_r[:, 3] == pos[:, 3])  # frozen atom never moves
+    assert np.all(out_g[:, 3] == 0)
+    # iteration limit: returns "failed" with the state reached
+    lim = fly.LBFGS(fly.lbfgs_options(iter_max=3))
+    out_r, out_g, failed, cnt = lim.minimise(s, pos, fly.Generic(data))
+    assert failed.all() and (cnt[:, 3] == 3).all() and (cnt[:, 0] == 4).all()
+    iopt = oracle_lib.LBFGS_IOPT.copy()
+    iopt[1] = 3
+    o_r, o_g, o_fail, o_cnt = osys.minimise_batch(pos, ids, fz2, threads=3, iopt=iopt)
+    assert np.abs(out_r - o_r).max() < 1e-9
+    s.close()
+
+
+def _check_dimer_against_oracle(fly, data, otab, ids, fz, ex, osys, r0, P, A, threads=8, **kw):
+    R = len(P)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=R)
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(s, P, A, r0, fly.Generic(data), **kw)
+    o_r, o_ax, o_code, o_cnt = osys.find_sp_batch(P, A, ids, fz, r0, threads=threads, **kw)
+    s.close()
+    assert code.tolist() == o_code.tolist()
+    E0 = _energy(osys, otab, ids, r0)
+    n_ok = 0
+    for k in range(R):
+        if code[k] == 0:
+            n_ok += 1
+            assert np.abs(out_r[k] - o_r[k]).max() < 1e-5
+            assert abs(abs((out_ax[k] * o_ax[k]).sum()) - 1) < 1e-3  # same unstable mode (sign is free; rotor theta_tol = 0.5 deg)
+            barrier_g = _energy(osys, otab, ids, out_r[k]) - E0
+            barrier_o = _energy(osys, otab, ids, o_r[k]) - E0
+            assert abs(barrier_g - barrier_o) < 1e-6  # north_star tolerance on saddle barriers
+            assert barrier_g > 0
+    return code, cnt, o_cnt, n_ok
+
+
+def test_dimer_matches_oracle_small(gpu, otab, small_cell):
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    code, cnt, o_cnt, n_ok = _check_dimer_against_oracle(fly, data, otab, ids, fz, ex, osys, r0, P, A)
+    assert n_ok >= 1
+    # work counters: same order of magnitude as the CPU path (trajectories agree until rounding separates them)
+    assert np.all(cnt[:, 0] > 0)
+    assert abs(int(cnt[:, 0].sum()) - int(o_cnt[:, 0].sum())) <= 0.2 * o_cnt[:, 0].sum()
+
+
+def test_dimer_c3_cell(gpu, otab, oracle_lib):
+    """apps/hydrogen-sized cell (6^3, 431 atoms, L ~ 3.1 list radii: many periodic images)."""
+    fly, ctx, data = gpu
+    base, ex, ids = bcc_vacancy(6, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    osys = oracle_lib.System(otab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=8)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(12)]
+    P = np.stack([s[0] for s in starts])
+    A = np.stack([s[1] for s in starts])
+    code, cnt, o_cnt, n_ok = _check_dimer_against_oracle(fly, data, otab, ids, fz, ex, osys, r0, P, A)
+    assert n_ok >= 2
+
+
+def test_dimer_history_collision_and_limits(gpu, otab, small_cell):
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    pot = fly.Generic(data)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(s, P, A, r0, pot)
+    found = [k for k in range(len(P)) if code[k] == 0]
+    assert found
+    # cache = the first found saddle; a wide collision cone sends every search that heads there home early
+    hist = out_r[found[0]][None]
+    theta = np.deg2rad(60.0)
+    r2, a2, code2, cnt2 = fly.Dimer().find_sp(s, P, A, r0, pot, hist_sp=hist, theta_tol=theta)
+    o_r, o_ax, o_code, o_cnt = osys.find_sp_batch(P, A, ids, fz, r0, hist_sp=hist, theta_tol=theta, threads=8)
+    assert code2.tolist() == o_code.tolist()
+    assert code2[found[0]] == fly.Dimer.collision
+    # step limit
+    lim = fly.Dimer(fly.dimer_options(max_steps=2))
+    r3, a3, code3, cnt3 = lim.find_sp(s, P, A, r0, pot)
+    assert (code3 == fly.Dimer.iter_max).all() and (cnt3[:, 3] == 2).all()
+    s.close()
+
+
+def test_dimer_frozen_no_projection(gpu, otab, small_cell):
+    """count_frozen > 0 switches trans_proj off (rotor.cpp:92-94,159-161); find.cpp:116 calls it that way."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    fz2 = fz.copy()
+    fz2[0] = 1
+    A2 = A.copy()
+    A2[:, 0] = 0
+    A2 /= np.sqrt((A2 ** 2).sum(axis=(1, 2)))[:, None, None]
+    P2 = P.copy()
+    P2[:, 0] = r0[0]
+    _check_dimer_against_oracle(fly, data, otab, ids, fz2, ex, osys, r0, P2[:4], A2[:4], threads=4, count_frozen=1)
+
+
+def test_host_loop_equals_device_loop(gpu, small_cell):
+    """OFLY_SEARCH_LOOP=host drives the same tick kernels from the host: bit-identical results."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    pot = fly.Generic(data)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
+    ref = fly.Dimer().find_sp(s, P, A, r0, pot)
+    os.environ["OFLY_SEARCH_LOOP"] = "host"
+    try:
+        alt = fly.Dimer().find_sp(s, P, A, r0, pot)
+    finally:
+        del os.environ["OFLY_SEARCH_LOOP"]
+    for a, b in zip(ref, alt):
+        assert np.array_equal(a, b)
+    s.close()
+
+
+def test_out_of_bounds_reported_per_replica(gpu, small_cell):
+    """A replica whose atoms overlap overruns the F(rho) table: status -5 (the reference throws
+    Spline::OutOfBounds, which Master catches and retries, find.cpp:718-722); the others are unaffected."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    bad = P[:3].copy()
+    bad[1, 1:40] = bad[1, 0] + np.linspace(0.01, 0.4, 39)[:, None]
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=3)
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(s, bad, A[:3], r0, fly.Generic(data))
+    assert code[1] == -5 and code[0] != -5 and code[2] != -5
+    with pytest.raises(fly.OutOfBounds):
+        fly.Dimer().find_sp(s, bad, A[:3], r0, fly.Generic(data), raise_oob=True)
+    s.close()
