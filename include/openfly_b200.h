@@ -59,6 +59,8 @@ void *ofly_ctx_stream(ofly_ctx *ctx);
 int ofly_ctx_synchronize(ofly_ctx *ctx);
 /* Number of kernels this context has launched so far. */
 long ofly_ctx_launch_count(ofly_ctx *ctx);
+/* Number of lock-step ticks (one gradient evaluation of every still-active replica each) the search calls have run. */
+long ofly_ctx_tick_count(ofly_ctx *ctx);
 
 /* ---- EAM tables: potential::DataEAM -------------------------------------------------------- */
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ofly_ctx_stream": (_vp, [_vp]),
     "ofly_ctx_synchronize": (C.c_int, [_vp]),
     "ofly_ctx_launch_count": (C.c_long, [_vp]),
+    "ofly_ctx_tick_count": (C.c_long, [_vp]),
     "ofly_tables_load_setfl": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "ofly_tables_retain": (None, [_vp]),
     "ofly_tables_release": (None, [_vp]),
@@ -105,7 +106,7 @@ SIGNATURES = {
 
 def build(verbose: bool = False) -> str:
     """Compile libopenfly_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", os.path.join(_PKG, "csrc")], capture_output=True, text=True)
+    res = subprocess.run(["make", "-j4", "-C", os.path.join(_PKG, "csrc")], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:], res.stderr[-4000:])
     if res.returncode != 0:

@@ -265,6 +265,7 @@ int ofly_ctx_synchronize(ofly_ctx *ctx) {
   });
 }
 long ofly_ctx_launch_count(ofly_ctx *ctx) { return ctx ? ctx->launches : 0; }
+long ofly_ctx_tick_count(ofly_ctx *ctx) { return ctx ? ctx->ticks : 0; }
 
 // ---- tables ------------------------------------------------------------------------------------
 int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out) {

@@ -53,6 +53,7 @@ struct ofly_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long launches = 0;
+  long ticks = 0;  // search ticks executed (search.cuh)
   int sm_count = 0;
   int max_smem_optin = 0;
 };

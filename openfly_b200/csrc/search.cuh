@@ -38,6 +38,8 @@ namespace ofly {
 
   constexpr int kMaxHist = 16;  // upper bound on L-BFGS memory
   constexpr int kMaxRed = 8;    // values per fused reduction
+  constexpr int kGramVals = 5;  // dot products per history pair of the single-pass L-BFGS step
+  constexpr int kGramMax = kGramVals * kMaxHist;
 
   // Exit / status codes beyond the reference's enums.
   constexpr int kStatusOutOfBounds = -5;
@@ -50,6 +52,8 @@ namespace ofly {
   struct CoreState {  // StepLBFGS (lbfgs_core.hpp:101-118): history fill + rho_j
     int k, pad;
     double rho[kMaxHist];
+    // Gram entries of the stored pairs, [j * n + k]: sy = s_j . y_k, yy = y_j . y_k (newton_step_gram)
+    double sy[kMaxHist * kMaxHist], yy[kMaxHist * kMaxHist];
   };
 
   struct RepState {
@@ -69,7 +73,8 @@ namespace ofly {
     int n_active, n_rebuild;  // entries in the selection lists for the grid kernels of this tick
     int ticket;               // teams that have finished their segment in this tick
     int tick;
-    int pad[4];
+    long long kernels;  // kernels executed so far (an IF-guarded rebuild only counts when it ran)
+    int pad[2];
   };
 
   struct SearchParams {
@@ -99,7 +104,10 @@ namespace ofly {
     int *active, *rebuild;  // [R] selection lists
     int max_ticks;
     int use_cond;
+    int gram;  // 1: single-pass L-BFGS step (newton_step_gram), 0: pass-per-pair two-loop (newton_step)
     cudaGraphConditionalHandle cond;
+    int use_cond_rebuild;  // the rebuild kernels of a tick sit in an IF node that is skipped when nobody asked
+    cudaGraphConditionalHandle cond_rebuild;
   };
 
   // ---- team = one CTA or a cluster of C CTAs ------------------------------------------------------
@@ -139,11 +147,24 @@ namespace ofly {
                  : "memory");
   }
 
+  // Shared-memory block of the single-pass L-BFGS step, one per CTA.
+  template <int C>
+  struct GramShared {
+    double sy[kMaxHist * kMaxHist], yy[kMaxHist * kMaxHist];  // working copies of CoreState::sy / yy
+    double rho[kMaxHist];
+    double part[16][kGramMax];   // per-warp partial sums (a CTA has at most 16 warps)
+    double slots[C][kGramMax];   // per-CTA sums posted by every CTA of the cluster
+    double out[kGramMax];        // team-wide sums, order index i (oldest pair first): {s_p.y_i, y_p.s_i, y_p.y_i, g.s_i, g.y_i}
+    double alpha[kMaxHist], w[kMaxHist], h0;
+    unsigned long long off[kMaxHist];  // element offset of pair i's row inside Core::s / Core::y
+  };
+
   template <int C>
   struct Team {
     int tid, nthreads, rank;
     double *red;    // shared: [2][C][kMaxRed] cluster slots, then [2][32][kMaxRed] warp partials
-    uint64_t *bar;  // shared: [2] mbarriers, one per slot buffer (clusters only)
+    uint64_t *bar;  // shared: [3] mbarriers: one per slot buffer, one for reduce_wide (clusters only)
+    GramShared<C> *gram = nullptr;
     int parity = 0;
     uint32_t phase = 0;  // bit p: parity the next wait on bar[p] looks for
 
@@ -161,7 +182,7 @@ namespace ofly {
     __device__ __forceinline__ void init() {
       if constexpr (C > 1) {
         if (threadIdx.x == 0) {
-          mbar_init(bar, 1), mbar_init(bar + 1, 1);
+          mbar_init(bar, 1), mbar_init(bar + 1, 1), mbar_init(bar + 2, 1);
           asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         cg::this_cluster().sync();
@@ -216,6 +237,42 @@ namespace ofly {
         }
       }
       parity ^= 1;
+    }
+
+    // Sum nv <= kGramMax values over the team. In: gram->part[warp][v] written by lane 0 of every warp;
+    // out: gram->out[v], readable by every thread on return. Single-buffered: at least one reduce<>() lies
+    // between two calls, which is what keeps a fast CTA from posting into slots a peer still reads.
+    __device__ __forceinline__ void reduce_wide(int nv) {
+      GramShared<C> &G = *gram;
+      const int nw = blockDim.x >> 5;
+      __syncthreads();
+      if constexpr (C == 1) {
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+          double x = 0;
+          for (int k = 0; k < nw; k++) x += G.part[k][v];
+          G.out[v] = x;
+        }
+      } else {
+        uint64_t *mb = bar + 2;
+        const uint32_t mbl = smem_u32(mb);
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+          double x = 0;
+          for (int k = 0; k < nw; k++) x += G.part[k][v];
+          const uint32_t slot = smem_u32(&G.slots[rank][v]);
+#pragma unroll
+          for (int c = 0; c < C; c++) dsmem_post(map_to_cta(slot, c), x, map_to_cta(mbl, c));
+        }
+        if (threadIdx.x == 0) mbar_expect_tx(mb, C * nv * 8);
+        mbar_wait(mb, (phase >> 2) & 1u);
+        phase ^= 4u;
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+          double x = 0;
+#pragma unroll
+          for (int c = 0; c < C; c++) x += G.slots[c][v];
+          G.out[v] = x;
+        }
+      }
+      __syncthreads();
     }
   };
 
@@ -358,149 +415,169 @@ namespace ofly {
     c.k++;
   }
 
-  // Same recursion with the running vector q held in registers: thread `tid` owns elements
-  // tid + e * nthreads, e < EPT, for the whole call, so a pass only streams the two history vectors it
-  // needs (all of a chunk's loads are in flight together) and q never round-trips through memory.
-  // Visiting order and arithmetic per element are those of newton_step: results are bit-identical.
-  // Requires n3 <= EPT * nthreads.
-  template <int C, int EPT>
-  __device__ __forceinline__ void newton_step_reg(Team<C> &tm, Core &c, const double *x, const double *g, int n3, const double *w,
-                                               double &out_nrm2, double &out_dotw) {
-    constexpr int CH = 8;  // elements whose loads are issued back to back
-    static_assert(EPT % CH == 0, "EPT must be a multiple of the chunk");
+  // StepLBFGS::newton_step in TWO streaming passes instead of one pass per history pair.
+  //
+  // The two-loop recursion only ever needs the running vector q through its dot products with the stored
+  // pairs, and q stays in span{g, y_k, s_k}. With the Gram entries s_j.y_k and y_j.y_k of the stored pairs
+  // (kept in CoreState, one row/column refreshed per step) plus s_k.g and y_k.g, every alpha_j / beta_j of
+  // lbfgs_core.cpp:57-82 is scalar arithmetic:
+  //   s_j.q = s_j.g - sum_{k newer than j} alpha_k s_j.y_k
+  //   y_j.r = h0 (y_j.g - sum_k alpha_k y_j.y_k) + sum_{k older than j} w_k s_k.y_j ,  w_k = alpha_k - beta_k
+  // Pass A streams the pairs once and accumulates the 5 dot products per pair that involve the newest pair
+  // or g; ONE team-wide reduction follows; thread 0 of each CTA runs the O(n^2) scalar recursion; pass B
+  // forms step = h0 (g - sum alpha_k y_k) + sum w_k s_k element by element in the two-loop's own operation
+  // order. The dependent chain per step is 2 passes + 2 reductions instead of 2n+2 of each -- the search is
+  // bound by exactly that chain once few replicas are left -- for the same bytes streamed.
+  // Differs from the two-loop only in how alpha/beta are rounded (scripts/lbfgs_gram_study.py).
+  template <int C>
+  __device__ __forceinline__ void newton_step_gram(Team<C> &tm, Core &c, const double *x, const double *g, int n3, const double *w,
+                                                double &out_nrm2, double &out_dotw) {
+    if (c.k == 0) return newton_step(tm, c, x, g, n3, w, out_nrm2, out_dotw);  // identity Hessian: one pass
+
+    constexpr int GS = 3;  // pairs per sweep of pass A (5 accumulators each)
+    constexpr int CH = 2;  // elements whose loads are issued back to back
+    GramShared<C> &G = *tm.gram;
     const int n = c.n;
-    const int prev = c.k > 0 ? (c.k - 1) % n : 0;
+    const int prev = (c.k - 1) % n;
     const int incur = c.k <= n ? 0 : c.k - n;
     const int bound = c.k <= n ? c.k : n;
     const int tid = tm.tid, nth = tm.nthreads;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *sp = c.s + (size_t)prev * c.n3p, *yp = c.y + (size_t)prev * c.n3p;
 
-    if (c.k == 0) return newton_step(tm, c, x, g, n3, w, out_nrm2, out_dotw);  // identity Hessian: one pass
+    // working copies of the persistent scalars (consumed after the reduction's barriers)
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) G.sy[t] = c.st->sy[t], G.yy[t] = c.st->yy[t];
+    if (threadIdx.x < n) G.rho[threadIdx.x] = c.st->rho[threadIdx.x];
 
-    double q[EPT];
-    double yy, d, rho_prev;
-    {  // newest pair (s, y), prev <- current, q <- g, first dot of loop 1
-      double *s = c.s + (size_t)prev * c.n3p, *y = c.y + (size_t)prev * c.n3p;
-      double a[3] = {0, 0, 0};
-#pragma unroll
-      for (int e0 = 0; e0 < EPT; e0 += CH / 2) {
-        double xv[CH / 2], gv[CH / 2], px[CH / 2], pg[CH / 2];
-#pragma unroll
-        for (int u = 0; u < CH / 2; u++) {
-          const int t = tid + (e0 + u) * nth;
-          if (t < n3) xv[u] = x[t], gv[u] = g[t], px[u] = c.prev_x[t], pg[u] = c.prev_g[t];
-        }
-#pragma unroll
-        for (int u = 0; u < CH / 2; u++) {
-          const int t = tid + (e0 + u) * nth;
-          if (t < n3) {
-            double sv = xv[u] - px[u], yv = gv[u] - pg[u];
-            s[t] = sv, y[t] = yv, c.prev_x[t] = xv[u], c.prev_g[t] = gv[u];
-            q[e0 + u] = gv[u];
-            a[0] = fma(sv, yv, a[0]), a[1] = fma(yv, yv, a[1]), a[2] = fma(sv, gv[u], a[2]);
-          }
-        }
-      }
-      tm.reduce<3>(a);
-      rho_prev = 1.0 / fabs(a[0]);
-      if (tid == 0) c.st->rho[prev] = rho_prev;
-      yy = a[1], d = a[2];
+    {  // newest pair (s, y); prev <- current   (lbfgs_core.cpp:37-52)
+      const double *const src[4] = {x, g, c.prev_x, c.prev_g};
+      team_pass<4>(tid, nth, n3, src, [&](int t, const double(&v)[4]) {
+        sp[t] = v[0] - v[2], yp[t] = v[1] - v[3], c.prev_x[t] = v[0], c.prev_g[t] = v[1];
+      });
     }
-    const double h0 = 1.0 / rho_prev / yy;
 
-    double alpha_of[kMaxHist];
-    // loop 1, newest -> oldest
-    for (int i = bound - 1; i >= 0; --i) {
-      const int j = (i + incur) % n;
-      const double rho_j = j == prev ? rho_prev : c.st->rho[j];
-      const double alpha = rho_j * d;
-      alpha_of[j] = alpha;
-      const double *y = c.y + (size_t)j * c.n3p;
-      const double *sn = i > 0 ? c.s + (size_t)((i - 1 + incur) % n) * c.n3p : y;  // last pair: dot with the same y after H0
-      const bool last = i == 0;
-      double a[1] = {0};
+    // pass A: every thread re-reads only its own elements of the newest pair
+    for (int i0 = 0; i0 < bound; i0 += GS) {
+      const double *sk[GS], *yk[GS];
 #pragma unroll
-      for (int e0 = 0; e0 < EPT; e0 += CH) {
-        double yv[CH], sv[CH];
+      for (int q = 0; q < GS; q++) {
+        const int i = min(i0 + q, bound - 1);  // a short last sweep repeats its last pair; those sums are dropped
+        const size_t row = (size_t)((i + incur) % n) * c.n3p;
+        sk[q] = c.s + row, yk[q] = c.y + row;
+      }
+      double acc[GS][kGramVals];
+#pragma unroll
+      for (int q = 0; q < GS; q++) {
+#pragma unroll
+        for (int d = 0; d < kGramVals; d++) acc[q][d] = 0;
+      }
+      for (int t0 = tid; t0 < n3; t0 += CH * nth) {
+        double vs[CH], vy[CH], vg[CH], hs[CH][GS], hy[CH][GS];
 #pragma unroll
         for (int u = 0; u < CH; u++) {
-          const int t = tid + (e0 + u) * nth;
+          const int t = t0 + u * nth;
           if (t < n3) {
-            yv[u] = y[t];
-            sv[u] = last ? yv[u] : sn[t];
+            vs[u] = sp[t], vy[u] = yp[t], vg[u] = g[t];
+#pragma unroll
+            for (int q = 0; q < GS; q++) hs[u][q] = sk[q][t], hy[u][q] = yk[q][t];
           }
         }
 #pragma unroll
         for (int u = 0; u < CH; u++) {
-          const int t = tid + (e0 + u) * nth;
+          const int t = t0 + u * nth;
           if (t < n3) {
-            double qv = fma(-alpha, yv[u], q[e0 + u]);
-            if (last) qv *= h0;
-            q[e0 + u] = qv;
-            a[0] = fma(sv[u], qv, a[0]);
+#pragma unroll
+            for (int q = 0; q < GS; q++) {
+              acc[q][0] = fma(vs[u], hy[u][q], acc[q][0]);
+              acc[q][1] = fma(vy[u], hs[u][q], acc[q][1]);
+              acc[q][2] = fma(vy[u], hy[u][q], acc[q][2]);
+              acc[q][3] = fma(vg[u], hs[u][q], acc[q][3]);
+              acc[q][4] = fma(vg[u], hy[u][q], acc[q][4]);
+            }
           }
         }
       }
-      tm.reduce<1>(a);
-      d = a[0];
-    }
-    // loop 2, oldest -> newest
-    for (int i = 0; i < bound; ++i) {
-      const int j = (i + incur) % n;
-      const double rho_j = j == prev ? rho_prev : c.st->rho[j];
-      const double coef = alpha_of[j] - rho_j * d;
-      const double *s = c.s + (size_t)j * c.n3p;
-      if (i + 1 < bound) {
-        const double *yn = c.y + (size_t)((i + 1 + incur) % n) * c.n3p;
-        double a[1] = {0};
 #pragma unroll
-        for (int e0 = 0; e0 < EPT; e0 += CH) {
-          double sv[CH], yv[CH];
+      for (int q = 0; q < GS; q++) {
 #pragma unroll
-          for (int u = 0; u < CH; u++) {
-            const int t = tid + (e0 + u) * nth;
-            if (t < n3) sv[u] = s[t], yv[u] = yn[t];
-          }
+        for (int d = 0; d < kGramVals; d++) {
+          double v = acc[q][d];
 #pragma unroll
-          for (int u = 0; u < CH; u++) {
-            const int t = tid + (e0 + u) * nth;
-            if (t < n3) {
-              double rv = fma(coef, sv[u], q[e0 + u]);
-              q[e0 + u] = rv;
-              a[0] = fma(yv[u], rv, a[0]);
-            }
-          }
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && i0 + q < bound) G.part[wid][kGramVals * (i0 + q) + d] = v;
         }
-        tm.reduce<1>(a);
-        d = a[0];
-      } else {
-        double a[2] = {0, 0};
-        double *out = c.step;
-#pragma unroll
-        for (int e0 = 0; e0 < EPT; e0 += CH) {
-          double sv[CH], wv[CH];
-#pragma unroll
-          for (int u = 0; u < CH; u++) {
-            const int t = tid + (e0 + u) * nth;
-            if (t < n3) {
-              sv[u] = s[t];
-              wv[u] = w ? w[t] : 0.0;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < CH; u++) {
-            const int t = tid + (e0 + u) * nth;
-            if (t < n3) {
-              double rv = fma(coef, sv[u], q[e0 + u]);
-              out[t] = rv;
-              a[0] = fma(rv, rv, a[0]);
-              if (w) a[1] = fma(rv, wv[u], a[1]);
-            }
-          }
-        }
-        tm.reduce<2>(a);
-        out_nrm2 = a[0], out_dotw = a[1];
       }
     }
+    tm.reduce_wide(kGramVals * bound);
+
+    if (threadIdx.x == 0) {  // identical inputs, identical arithmetic on every CTA of the team
+      const int p = prev;
+      for (int i = 0; i < bound; i++) {
+        const int j = (i + incur) % n;
+        const double *v = G.out + kGramVals * i;
+        G.sy[p * n + j] = v[0], G.sy[j * n + p] = v[1], G.yy[p * n + j] = v[2], G.yy[j * n + p] = v[2];
+        G.off[i] = (unsigned long long)j * c.n3p;
+      }
+      const double rho_p = 1.0 / fabs(G.sy[p * n + p]);  // abs: never an ascent direction (lbfgs_core.cpp:50)
+      G.rho[p] = rho_p;
+      const double h0 = 1.0 / rho_p / G.yy[p * n + p];   // initial Hessian scaling (lbfgs_core.cpp:70)
+      G.h0 = h0;
+      for (int i = bound - 1; i >= 0; --i) {  // loop 1, newest -> oldest
+        const int j = (i + incur) % n;
+        double sq = G.out[kGramVals * i + 3];
+        for (int i2 = bound - 1; i2 > i; --i2) sq = fma(-G.alpha[i2], G.sy[j * n + (i2 + incur) % n], sq);
+        G.alpha[i] = G.rho[j] * sq;
+      }
+      for (int i = 0; i < bound; ++i) {  // loop 2, oldest -> newest
+        const int j = (i + incur) % n;
+        double yq = G.out[kGramVals * i + 4];
+        for (int i2 = bound - 1; i2 >= 0; --i2) yq = fma(-G.alpha[i2], G.yy[j * n + (i2 + incur) % n], yq);
+        double yr = yq * h0;
+        for (int i2 = 0; i2 < i; ++i2) yr = fma(G.w[i2], G.sy[((i2 + incur) % n) * n + j], yr);
+        G.w[i] = G.alpha[i] - G.rho[j] * yr;
+      }
+      if (tm.rank == 0) {  // persist the refreshed row / column
+        c.st->rho[p] = rho_p;
+        for (int i = 0; i < bound; i++) {
+          const int j = (i + incur) % n;
+          c.st->sy[p * n + j] = G.sy[p * n + j], c.st->sy[j * n + p] = G.sy[j * n + p];
+          c.st->yy[p * n + j] = G.yy[p * n + j], c.st->yy[j * n + p] = G.yy[j * n + p];
+        }
+      }
+    }
+    __syncthreads();
+
+    // pass B: step = (g - sum alpha_k y_k) h0 + sum w_k s_k, accumulated newest->oldest then oldest->newest
+    const double h0 = G.h0;
+    double *out = c.step;
+    double a[2] = {0, 0};
+    for (int t = tid; t < n3; t += nth) {
+      double h[kMaxHist];
+#pragma unroll
+      for (int i = 0; i < kMaxHist; i++) {
+        if (i < bound) h[i] = c.y[G.off[i] + t];
+      }
+      double q = g[t];
+      const double wv = w ? w[t] : 0.0;
+#pragma unroll
+      for (int i = kMaxHist - 1; i >= 0; --i) {
+        if (i < bound) q = fma(-G.alpha[i], h[i], q);
+      }
+      q *= h0;
+#pragma unroll
+      for (int i = 0; i < kMaxHist; i++) {
+        if (i < bound) h[i] = c.s[G.off[i] + t];
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxHist; i++) {
+        if (i < bound) q = fma(G.w[i], h[i], q);
+      }
+      out[t] = q;
+      a[0] = fma(q, q, a[0]);
+      if (w) a[1] = fma(q, wv, a[1]);
+    }
+    tm.reduce<2>(a);
+    out_nrm2 = a[0], out_dotw = a[1];
     c.k++;
   }
 
@@ -534,7 +611,7 @@ namespace ofly {
 
   // One replica's segment: everything between two gradient requests. All threads of the team run the
   // same control flow on identical scalars; thread 0 stores the state that must survive the tick.
-  template <int C, int EPT>
+  template <int C>
   struct Segment {
     Team<C> &tm;
     const BatchDev &B;
@@ -578,11 +655,8 @@ namespace ofly {
     static __device__ __forceinline__ int pos_slot(int t) { return t + t / 3; }
 
     __device__ __forceinline__ void lbfgs_step(Core &c, const double *x, const double *g, const double *w, double &nrm2, double &dotw) {
-      if constexpr (EPT > 0) {
-        newton_step_reg<C, EPT>(tm, c, x, g, n3, w, nrm2, dotw);
-      } else {
-        newton_step(tm, c, x, g, n3, w, nrm2, dotw);
-      }
+      if (P.gram) return newton_step_gram<C>(tm, c, x, g, n3, w, nrm2, dotw);
+      newton_step(tm, c, x, g, n3, w, nrm2, dotw);
     }
 
     // Suspend until the gradient of the current list positions is in `dst`; resume at `phase`.
@@ -905,14 +979,15 @@ namespace ofly {
   // One tick's vector algebra: gridDim.x = R * C, team t owns replica t.
   // MAXT = 512: large systems, up to 128 registers so the batched loads of team_pass stay in registers;
   // MAXT = 128: small systems with thousands of replicas, 8 teams resident per SM.
-  // EPT > 0: n3 <= EPT * team threads, L-BFGS runs with q in registers; EPT = 0: any size.
-  template <int C, int MAXT, int EPT>
+  template <int C, int MAXT>
   __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 4 : 1) k_segment(BatchDev B, SearchParams P) {
     __shared__ double red_smem[team_smem_doubles(C)];
-    __shared__ uint64_t red_bar[2];
+    __shared__ uint64_t red_bar[3];
+    __shared__ GramShared<C> gram_smem;
     __shared__ int last_team;
 
     Team<C> tm(red_smem, red_bar);
+    tm.gram = &gram_smem;
     const int r = blockIdx.x / C;
     const int n_teams = gridDim.x / C;
 
@@ -920,7 +995,7 @@ namespace ofly {
     if (phase != kDone) {
       tm.init();
       const int fault = __ldcg(B.fault + r);
-      Segment<C, EPT> seg(tm, B, P, r);
+      Segment<C> seg(tm, B, P, r);
       if (phase != kInit && (fault & kFaultCapacity)) {
         seg.finish(kStatusCapacity);
       } else if (phase != kInit && (fault & kFaultOutOfBounds)) {
@@ -969,8 +1044,10 @@ namespace ofly {
         }
         if (lane == 0) {
           P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;
+          P.ctl->kernels += 3 + ((!P.use_cond_rebuild || nr > 0) ? 5 : 0);
           __threadfence();
           if (P.use_cond) cudaGraphSetConditional(P.cond, (na > 0 && tick <= P.max_ticks) ? 1u : 0u);
+          if (P.use_cond_rebuild) cudaGraphSetConditional(P.cond_rebuild, nr > 0 ? 1u : 0u);
         }
       }
     }

@@ -1,6 +1,7 @@
 // C ABI: minimise::LBFGS::minimise and saddle::Dimer::find_sp over a whole batch (search.cuh).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -34,8 +35,6 @@ namespace ofly {
     }
 
     constexpr int kSegMaxThreads = 512;
-    constexpr int kSegEpt = 16;         // elements per thread the register-resident L-BFGS step can hold
-    constexpr int kTickNodes = 8;       // kernels per tick
     constexpr int kHostLoopTicks = 8;   // ticks between host checks when the device-side loop is off
 
     int env_int(char const *name, int dflt) {
@@ -61,7 +60,7 @@ namespace ofly {
       return t;
     }
 
-    template <int C, int MAXT, int EPT>
+    template <int C, int MAXT>
     void launch_segment(ofly_ctx *ctx, int teams, int threads, BatchDev const &B, SearchParams const &P) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(teams * C));
@@ -73,80 +72,111 @@ namespace ofly {
       attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = C > 1 ? 1 : 0;
-      OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT, EPT>, B, P));
+      OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT>, B, P));
     }
 
     unsigned stride_grid(ofly_ctx *ctx, size_t items, int per_sm) {
       return (unsigned)std::max<size_t>(1, std::min<size_t>(items, (size_t)ctx->sm_count * per_sm));
     }
 
-    // One tick: segment, rebuild of the flagged replicas, gradient of the active ones (search.cuh).
-    void enqueue_tick(ofly_batch *b, SearchParams const &P, TeamShape shape) {
+    // One tick = segment, rebuild of the flagged replicas, gradient of the active ones (search.cuh), enqueued in
+    // three parts so that the device-side loop can put the rebuild kernels behind an IF node.
+    void enqueue_segment(ofly_batch *b, SearchParams const &P, TeamShape shape) {
       ofly_ctx *ctx = b->ctx;
-      cudaStream_t st = ctx->stream;
       BatchDev const &B = b->d;
-      TablesDev const &T = b->tables->dev;
-      const size_t atoms = (size_t)b->R * b->N;
-      const bool in_regs = 3 * b->N <= (long)kSegEpt * shape.threads * shape.cluster;
       const int teams = (int)b->R;
-#define OFLY_SEG(C, T)                                                   \
-  if (in_regs) {                                                         \
-    launch_segment<C, T, kSegEpt>(ctx, teams, shape.threads, B, P);      \
-  } else {                                                               \
-    launch_segment<C, T, 0>(ctx, teams, shape.threads, B, P);            \
-  }
       switch (shape.cluster) {
         case 8:
-          OFLY_SEG(8, kSegMaxThreads);
+          launch_segment<8, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
           break;
         case 4:
-          OFLY_SEG(4, kSegMaxThreads);
+          launch_segment<4, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
           break;
         case 2:
-          OFLY_SEG(2, kSegMaxThreads);
+          launch_segment<2, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
           break;
         default:
           if (shape.threads <= 128) {
-            OFLY_SEG(1, 128);
+            launch_segment<1, 128>(ctx, teams, shape.threads, B, P);
           } else {
-            OFLY_SEG(1, kSegMaxThreads);
+            launch_segment<1, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
           }
           break;
       }
-#undef OFLY_SEG
-      Sel reb{P.rebuild, &P.ctl->n_rebuild}, act{P.active, &P.ctl->n_active};
+    }
+
+    struct PairGrid {
+      int G;
+      unsigned blocks;
+    };
+    PairGrid pair_grid(ofly_batch *b) {
+      const size_t atoms = (size_t)b->R * b->N;
+      const int G = pick_group(b->ctx, (long)atoms);
+      const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
+      return {G, stride_grid(b->ctx, tiles, 8)};
+    }
+
+    void enqueue_rebuild(ofly_batch *b, SearchParams const &P) {
+      ofly_ctx *ctx = b->ctx;
+      cudaStream_t st = ctx->stream;
+      BatchDev const &B = b->d;
+      const size_t atoms = (size_t)b->R * b->N;
+      Sel reb{P.rebuild, &P.ctl->n_rebuild};
       k_nb_canon_count<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb, P.ws, P.ws_stride);
       k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(B, reb);
       k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb);
       k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
-      const unsigned long long *goff = &P.state->gdst;
-      const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
-      const int G = pick_group(ctx, (long)atoms);
-      const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
-      const unsigned gg = stride_grid(ctx, tiles, 8);
-      switch (G) {
+      const PairGrid pg = pair_grid(b);
+      switch (pg.G) {
         case 32:
-          k_nb_build<32><<<gg, 256, 0, st>>>(B, reb);
-          k_eam_rho<32><<<gg, 256, 0, st>>>(B, T, act);
-          k_eam_force<32><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          k_nb_build<32><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
         case 16:
-          k_nb_build<16><<<gg, 256, 0, st>>>(B, reb);
-          k_eam_rho<16><<<gg, 256, 0, st>>>(B, T, act);
-          k_eam_force<16><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          k_nb_build<16><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
         case 8:
-          k_nb_build<8><<<gg, 256, 0, st>>>(B, reb);
-          k_eam_rho<8><<<gg, 256, 0, st>>>(B, T, act);
-          k_eam_force<8><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          k_nb_build<8><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
         default:
-          k_nb_build<4><<<gg, 256, 0, st>>>(B, reb);
-          k_eam_rho<4><<<gg, 256, 0, st>>>(B, T, act);
-          k_eam_force<4><<<gg, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          k_nb_build<4><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
       }
       OFLY_CUDA(cudaGetLastError());
+    }
+
+    void enqueue_gradient(ofly_batch *b, SearchParams const &P) {
+      cudaStream_t st = b->ctx->stream;
+      BatchDev const &B = b->d;
+      TablesDev const &T = b->tables->dev;
+      Sel act{P.active, &P.ctl->n_active};
+      const unsigned long long *goff = &P.state->gdst;
+      const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
+      const PairGrid pg = pair_grid(b);
+      switch (pg.G) {
+        case 32:
+          k_eam_rho<32><<<pg.blocks, 256, 0, st>>>(B, T, act);
+          k_eam_force<32><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        case 16:
+          k_eam_rho<16><<<pg.blocks, 256, 0, st>>>(B, T, act);
+          k_eam_force<16><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        case 8:
+          k_eam_rho<8><<<pg.blocks, 256, 0, st>>>(B, T, act);
+          k_eam_force<8><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        default:
+          k_eam_rho<4><<<pg.blocks, 256, 0, st>>>(B, T, act);
+          k_eam_force<4><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+      }
+      OFLY_CUDA(cudaGetLastError());
+    }
+
+    void enqueue_tick(ofly_batch *b, SearchParams const &P, TeamShape shape) {
+      enqueue_segment(b, P, shape);
+      enqueue_rebuild(b, P);
+      enqueue_gradient(b, P);
     }
 
     struct GraphGuard {
@@ -158,35 +188,97 @@ namespace ofly {
       }
     };
 
-    // The whole search as ONE graph launch: a WHILE conditional node whose body is one tick; the
-    // segment kernel clears the condition when no replica is active.
-    void run_device_loop(ofly_batch *b, SearchParams P, TeamShape shape) {
+    // Ends a capture that an exception interrupted, then rethrows.
+    struct CaptureScope {
+      cudaStream_t st;
+      bool open = true;
+      explicit CaptureScope(cudaStream_t s) : st(s) {}
+      void end() {
+        open = false;
+        OFLY_CUDA(cudaStreamEndCapture(st, nullptr));
+      }
+      ~CaptureScope() {
+        if (open) {
+          cudaGraph_t dead = nullptr;
+          cudaStreamEndCapture(st, &dead);
+        }
+      }
+    };
+
+    // The whole search as ONE graph launch: a WHILE conditional node whose body is one tick; the segment
+    // kernel clears the condition when no replica is active. With `nested` the five rebuild kernels sit in
+    // an IF node inside the body that the segment kernel arms only when some replica asked for a rebuild
+    // (late in a batch most ticks have none, and five empty launches are a sixth of such a tick).
+    // Returns false if the graph could not be constructed (nothing was launched).
+    bool try_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, bool nested) {
       ofly_ctx *ctx = b->ctx;
       GraphGuard g;
-      OFLY_CUDA(cudaGraphCreate(&g.graph, 0));
-      cudaGraphConditionalHandle handle;
-      OFLY_CUDA(cudaGraphConditionalHandleCreate(&handle, g.graph, 1, cudaGraphCondAssignDefault));
-      cudaGraphNodeParams np{};
-      np.type = cudaGraphNodeTypeConditional;
-      np.conditional.handle = handle;
-      np.conditional.type = cudaGraphCondTypeWhile;
-      np.conditional.size = 1;
-      cudaGraphNode_t node;
-      OFLY_CUDA(cudaGraphAddNode(&node, g.graph, nullptr, 0, &np));
-      cudaGraph_t body = np.conditional.phGraph_out[0];
-      P.use_cond = 1, P.cond = handle;
-      OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
       try {
-        enqueue_tick(b, P, shape);
-      } catch (...) {
-        cudaGraph_t dead = nullptr;
-        cudaStreamEndCapture(ctx->stream, &dead);
-        throw;
+        OFLY_CUDA(cudaGraphCreate(&g.graph, 0));
+        cudaGraphConditionalHandle handle, handle_if{};
+        OFLY_CUDA(cudaGraphConditionalHandleCreate(&handle, g.graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np{};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        OFLY_CUDA(cudaGraphAddNode(&node, g.graph, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        P.use_cond = 1, P.cond = handle;
+        cudaGraph_t if_body = nullptr;
+        if (nested) {
+          OFLY_CUDA(cudaGraphConditionalHandleCreate(&handle_if, g.graph, 0, cudaGraphCondAssignDefault));
+          P.use_cond_rebuild = 1, P.cond_rebuild = handle_if;
+        }
+        {
+          OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+          CaptureScope cap(ctx->stream);
+          enqueue_segment(b, P, shape);
+          if (nested) {
+            cudaStreamCaptureStatus status;
+            const cudaGraphNode_t *deps = nullptr;
+            size_t n_deps = 0;
+            OFLY_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, nullptr, &deps, &n_deps));
+            cudaGraphNodeParams ip{};
+            ip.type = cudaGraphNodeTypeConditional;
+            ip.conditional.handle = handle_if;
+            ip.conditional.type = cudaGraphCondTypeIf;
+            ip.conditional.size = 1;
+            cudaGraphNode_t if_node;
+            OFLY_CUDA(cudaGraphAddNode(&if_node, body, deps, n_deps, &ip));
+            if_body = ip.conditional.phGraph_out[0];
+            OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
+          } else {
+            enqueue_rebuild(b, P);
+          }
+          enqueue_gradient(b, P);
+          cap.end();
+        }
+        if (nested) {
+          OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, if_body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+          CaptureScope cap(ctx->stream);
+          enqueue_rebuild(b, P);
+          cap.end();
+        }
+        OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+      } catch (Error const &e) {
+        cudaGetLastError();
+        if (!nested) throw;
+        if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: nested rebuild IF node unavailable (%s); flat tick graph\n", e.what());
+        return false;
       }
-      OFLY_CUDA(cudaStreamEndCapture(ctx->stream, nullptr));
-      OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+      if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: search graph with %s rebuild\n", nested ? "IF-guarded" : "unconditional");
       OFLY_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
       OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+      return true;
+    }
+
+    void run_device_loop(ofly_batch *b, SearchParams P, TeamShape shape) {
+      char const *v = std::getenv("OFLY_REBUILD_IF");
+      const bool nested = !(v && std::string(v) == "0");
+      if (nested && try_device_loop(b, P, shape, true)) return;
+      try_device_loop(b, P, shape, false);
     }
 
     // Fallback / profiling mode (OFLY_SEARCH_LOOP=host): plain launches, the host looks at the active
@@ -246,6 +338,11 @@ namespace ofly {
       const long per_step = P.mode == 0 ? 1 : 2 + 10L * std::max(1, P.iter_max_rot) + 2;
       P.max_ticks = (int)std::min<long>((long)(P.iter_max + 1) * per_step + 8, 1L << 30);
 
+      // OFLY_LBFGS=twoloop selects the pass-per-pair recursion (A/B comparisons); default is the single-pass step.
+      P.gram = [] {
+        char const *v = std::getenv("OFLY_LBFGS");
+        return !(v && std::string(v) == "twoloop");
+      }();
       const bool device_loop = [] {
         char const *v = std::getenv("OFLY_SEARCH_LOOP");
         return !(v && std::string(v) == "host");
@@ -263,7 +360,8 @@ namespace ofly {
         b->built = true;
         // The fault words double as the capacity report; reading them is the call's synchronisation.
         int f = collect_faults(b);
-        ctx->launches += (long)c.tick * kTickNodes;  // kernels executed (by the device-side loop or the host loop)
+        ctx->launches += (long)c.kernels;  // kernels executed (by the device-side loop or the host loop)
+        ctx->ticks += c.tick;
         if (c.n_active != 0) throw Error(OFLY_ERR_CUDA, "search loop ended with active replicas");
         if (!(f & kFaultCapacity)) break;
         if (attempt == 2) throw Error(OFLY_ERR_CAPACITY, "neighbour buffers overflowed after regrowing");

@@ -45,6 +45,9 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.ofly_ctx_launch_count(self.h))
 
+    def tick_count(self) -> int:
+        return int(self.lib.ofly_ctx_tick_count(self.h))
+
     def close(self) -> None:
         if self.h:
             self.lib.ofly_ctx_destroy(self.h)

@@ -684,6 +684,9 @@ namespace oracle {
     void clear() { m_k = 0; }
 
     Arr &newton_step(Arr const &r, Arr const &g) {
+#ifdef FLY_ORACLE_LBFGS_GRAM
+      return newton_step_gram(r, g);
+#endif
       int prev = (m_k - 1) % m_n;
       m_r.resize(r.size());
       if (m_k > 0) {
@@ -722,6 +725,83 @@ namespace oracle {
       ++m_k;
       return m_r;
     }
+
+#ifdef FLY_ORACLE_LBFGS_GRAM
+    // STUDY VARIANT, never part of the oracle builds (scripts/lbfgs_gram_study.py defines the macro):
+    // the same recursion with every dot product s_j.q / y_j.r expanded over the Gram entries
+    // s_j.y_k, y_j.y_k, s_j.g, y_j.g (what the device computes in ONE pass, search.cuh newton_step),
+    // followed by the element-wise combination in the two-loop's own operation order. Used to check
+    // that the re-association only perturbs trajectories at rounding level.
+    Arr &newton_step_gram(Arr const &r, Arr const &g) {
+      int n = m_n;
+      int prev = m_k > 0 ? (m_k - 1) % n : 0;
+      m_r.resize(r.size());
+      if (m_sy.empty()) m_sy.assign(n * n, 0.0), m_yy.assign(n * n, 0.0);
+      if (m_k > 0) {
+        Elem &e = m_hist[prev];
+        e.s.resize(r.size()), e.y.resize(r.size());
+        for (std::size_t i = 0; i < r.size(); i++) e.s[i] = r[i] - m_prev_x[i], e.y[i] = g[i] - m_prev_g[i];
+      }
+      m_prev_x = r, m_prev_g = g;
+      int incur = m_k <= n ? 0 : m_k - n;
+      int bound = m_k <= n ? m_k : n;
+      if (m_k == 0) {
+        m_r = g;
+        ++m_k;
+        return m_r;
+      }
+      std::vector<double> sg(n), yg(n);
+      for (int i = 0; i < bound; i++) {
+        int k = (i + incur) % n;
+        m_sy[prev * n + k] = dot(m_hist[prev].s, m_hist[k].y);
+        m_sy[k * n + prev] = dot(m_hist[k].s, m_hist[prev].y);
+        m_yy[prev * n + k] = m_yy[k * n + prev] = dot(m_hist[prev].y, m_hist[k].y);
+        sg[k] = dot(m_hist[k].s, g), yg[k] = dot(m_hist[k].y, g);
+      }
+      m_hist[prev].rho = 1.0 / std::abs(m_sy[prev * n + prev]);
+      double h0 = 1.0 / m_hist[prev].rho / m_yy[prev * n + prev];
+      std::vector<double> w(n);
+      for (int i = bound - 1; i >= 0; --i) {
+        int j = (i + incur) % n;
+        double sq = sg[j];
+        for (int i2 = bound - 1; i2 > i; --i2) {
+          int k = (i2 + incur) % n;
+          sq -= m_hist[k].alpha * m_sy[j * n + k];
+        }
+        m_hist[j].alpha = m_hist[j].rho * sq;
+      }
+      for (int i = 0; i < bound; ++i) {
+        int j = (i + incur) % n;
+        double yq = yg[j];
+        for (int i2 = bound - 1; i2 >= 0; --i2) {
+          int k = (i2 + incur) % n;
+          yq -= m_hist[k].alpha * m_yy[j * n + k];
+        }
+        double yr = yq * h0;
+        for (int i2 = 0; i2 < i; ++i2) {
+          int k = (i2 + incur) % n;
+          yr += w[k] * m_sy[k * n + j];
+        }
+        w[j] = m_hist[j].alpha - m_hist[j].rho * yr;
+      }
+      for (std::size_t t = 0; t < m_r.size(); t++) {
+        double q = g[t];
+        for (int i = bound - 1; i >= 0; --i) {
+          int j = (i + incur) % n;
+          q -= m_hist[j].alpha * m_hist[j].y[t];
+        }
+        q *= h0;
+        for (int i = 0; i < bound; ++i) {
+          int j = (i + incur) % n;
+          q += w[j] * m_hist[j].s[t];
+        }
+        m_r[t] = q;
+      }
+      ++m_k;
+      return m_r;
+    }
+    std::vector<double> m_sy, m_yy;
+#endif
 
   private:
     struct Elem {

@@ -186,6 +186,45 @@ def test_host_loop_equals_device_loop(gpu, small_cell):
     s.close()
 
 
+def test_single_pass_lbfgs_equals_two_loop(gpu, otab, small_cell):
+    """The default L-BFGS step (Gram entries, two passes per step: search.cuh newton_step_gram) against the
+    pass-per-pair two-loop recursion (OFLY_LBFGS=twoloop, the literal lbfgs_core.cpp:29-87 order): the two
+    round alpha/beta differently, so trajectories agree to rounding: same exits, same saddles."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    pot = fly.Generic(data)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
+    new = fly.Dimer().find_sp(s, P, A, r0, pot)
+    os.environ["OFLY_LBFGS"] = "twoloop"
+    try:
+        old = fly.Dimer().find_sp(s, P, A, r0, pot)
+    finally:
+        del os.environ["OFLY_LBFGS"]
+    assert new[2].tolist() == old[2].tolist()
+    for k in range(len(P)):
+        if new[2][k] == 0:
+            assert np.abs(new[0][k] - old[0][k]).max() < 1e-5
+    assert abs(int(new[3][:, 0].sum()) - int(old[3][:, 0].sum())) <= 0.2 * old[3][:, 0].sum()
+    s.close()
+
+
+def test_rebuild_if_node_equals_flat_graph(gpu, small_cell):
+    """OFLY_REBUILD_IF=0 keeps the five rebuild kernels unconditional in every tick: bit-identical results."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    pot = fly.Generic(data)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
+    ref = fly.Dimer().find_sp(s, P, A, r0, pot)
+    os.environ["OFLY_REBUILD_IF"] = "0"
+    try:
+        alt = fly.Dimer().find_sp(s, P, A, r0, pot)
+    finally:
+        del os.environ["OFLY_REBUILD_IF"]
+    for a, b in zip(ref, alt):
+        assert np.array_equal(a, b)
+    s.close()
+
+
 def test_out_of_bounds_reported_per_replica(gpu, small_cell):
     """A replica whose atoms overlap overruns the F(rho) table: status -5 (the reference throws
     Spline::OutOfBounds, which Master catches and retries, find.cpp:718-722); the others are unaffected."""
