@@ -55,6 +55,8 @@ namespace ofly {
       if (t.threads == kSegMaxThreads) {
         while (t.cluster < 8 && n3 > (long)t.cluster * t.threads * 8) t.cluster *= 2;
       }
+      int ft = env_int("OFLY_TEAM_THREADS", 0);  // tuning overrides
+      if (ft == 128 || ft == 256 || ft == 512) t.threads = ft, t.cluster = 1;
       int forced = env_int("OFLY_CLUSTER", 0);
       if (forced == 1 || forced == 2 || forced == 4 || forced == 8) t.cluster = forced;
       return t;

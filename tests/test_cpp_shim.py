@@ -1,0 +1,71 @@
+"""The C++20 host shim (include/openfly_b200/fly.hpp) -- the reference's class surface for a compiled host.
+CPU: the header compiles with -std=c++20, links against the C-ABI library and its host-only calls work.
+GPU: examples/shim_demo.cpp (List / Generic / LBFGS / Dimer through the shim) against the CPU oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.common import ROOT, WEN, bcc_vacancy
+
+DEMO = os.path.join(ROOT, "examples", "shim_demo")
+
+
+@pytest.fixture(scope="module")
+def demo():
+    from openfly_b200 import capi
+
+    capi.build()
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, capture_output=True)
+    return DEMO
+
+
+def test_shim_compiles_links_and_runs_host_only(demo):
+    out = subprocess.run([demo, "--host-only", WEN], check=True, capture_output=True, text=True).stdout
+    d = json.loads(out)
+    assert d["version"].startswith("openfly_b200")
+    assert (d["lbfgs_n"], d["dimer_n"], d["rotor_n"], d["types"], d["knots_r"], d["r_cut"]) == (10, 10, 6, 2, 10004, 5.3)
+
+
+def test_shim_reports_errors_as_exceptions(demo):
+    res = subprocess.run([demo, "--host-only", "/nonexistent.eam.fs"], capture_output=True, text=True)
+    assert res.returncode == 1 and "error:" in res.stderr
+
+
+@pytest.mark.gpu
+def test_shim_demo_matches_oracle(demo, oracle_lib, tmp_path):
+    cells, R = 4, 4
+    base, ex, ids = bcc_vacancy(cells, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    tab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(tab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=4)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(R)]
+    path = tmp_path / "starts.bin"
+    np.stack([np.stack([s[0], s[1]]) for s in starts]).astype(np.float64).tofile(path)
+
+    out = subprocess.run([demo, WEN, str(cells), str(R), str(path)], check=True, capture_output=True, text=True).stdout
+    d = json.loads(out)
+    assert d["atoms"] == len(ids) and d["launches"] > 0
+
+    osys.rebuild(tab.rcut, base)
+    E = osys.energy(ids)
+    assert abs(d["energy"] - E) <= 1e-10 * abs(E)
+    assert abs(d["grad_max"] - np.abs(osys.gradient(ids, fz)).max()) < 1e-9
+    assert d["neigh0"] == len(osys.for_neighbours(0, tab.rcut)[0])
+    assert d["min_failed"] == 0
+    osys.rebuild(tab.rcut, r0)
+    assert abs(d["energy_min"] - osys.energy(ids)) < 1e-9
+    res = np.fromfile(str(path) + ".out", dtype=np.float64)
+    n3 = 3 * len(ids)
+    assert np.abs(res[:n3].reshape(-1, 3) - r0).max() < 1e-6
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    o_r, _, o_code, _ = osys.find_sp_batch(P, A, ids, fz, r0, threads=4)
+    assert d["exits"] == o_code.tolist()
+    sp = res[n3:].reshape(R, -1, 3)
+    for k in range(R):
+        if o_code[k] == 0:
+            assert np.abs(sp[k] - o_r[k]).max() < 1e-5
