@@ -4,13 +4,15 @@
 Workload (BASELINE.json configs[1], "C2"): bcc Fe 20x20x20 (a = 2.8553), one vacancy, one H -> 16 000 atoms;
 a batch of 64 concurrent dimer saddle searches started from Master::perturb-style states around the H atom.
 One *step* = one Dimer::find_sp over the whole batch (reference default options), i.e. every neighbour
-rebuild/update, EAM gradient, rotor and L-BFGS update of 64 searches, all inside one persistent kernel.
+rebuild/update, EAM gradient, rotor and L-BFGS update of 64 searches, as ONE CUDA-graph launch whose body (a tick:
+vector algebra of every active replica, rebuilds, one gradient evaluation) repeats on the device.
 
   value  = EAM atom-gradient evaluations / s inside the step, inputs resident in HBM (ofly_dimer_find_sp_dev)
   e2e    = same metric through the host-pointer C-ABI call (ofly_dimer_find_sp): pinned host inputs are copied
            to the device and positions/axes/exit codes are copied back inside the timed region
-  roofline: algorithmic bytes (8 n + 64 per atom-gradient eval, n = measured mean stored neighbours) over the
-           CUDA-event duration of the persistent search kernel, against MEASURED_PEAKS.json's HBM figure
+  roofline: the dominant kernels, k_eam_rho + k_eam_force (one gradient evaluation of the resident batch), timed
+           live with CUDA events on the library's stream; algorithmic bytes (8 n + 64 per atom-gradient eval, n =
+           measured mean stored neighbours) against MEASURED_PEAKS.json's HBM figure
   cpu_baseline / --impl reference: the CPU oracle built with the reference's flags, all host cores, one
            single-threaded search per core exactly like saddle::Master (src/saddle/find.cpp:698,990)
 
@@ -38,6 +40,9 @@ CELLS, LATTICE, REPLICAS = 20, 2.8553, 64
 METRIC, UNIT = "eam_atom_gradient_evals_per_s", "atom-evals/s"
 WORKLOAD = "C2: bcc Fe 20^3 (a=2.8553) - 1 vacancy + 1 H = 16000 atoms, Wen Fe-H EAM, 64 concurrent dimer searches (Dimer::find_sp, default options)"
 CPU_SAMPLE_MAX_STEPS = 40  # translation steps per CPU search in the bounded sample
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_rho + k_eam_force launch pair on this workload, from the ncu --set full
+# capture summarised in profiles/ (None until a capture of the current kernels is committed)
+NCU_TRAFFIC = None
 
 
 def peaks():
@@ -155,7 +160,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    launches0 = ctx.launch_count()
+    launches0, ticks0 = ctx.launch_count(), ctx.tick_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         ev0.record(stream)
@@ -163,7 +168,7 @@ def run_b200(args):
             step_dev()
         ev1.record(stream)
         barrier()
-    launches = ctx.launch_count() - launches0
+    launches, ticks = ctx.launch_count() - launches0, ctx.tick_count() - ticks0
     ms_total = ev0.elapsed_time(ev1)
 
     cnt = np.zeros((R, 4), dtype=np.int64)
@@ -193,26 +198,23 @@ def run_b200(args):
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(hcode, code), "host-buffer and device-resident calls disagree"
 
-    # isolated gradient launches on the resident batch (roofline study of the pair kernels)
-    grad_leg = None
-    if world == 1:
-        r_list = data.rcut() + 2 * ropt.delta_r
-        r_list += max(dopt.skin_frac ** (1 / 3) - 1, 0) * r_list
-        capi.check(lib.ofly_neigh_rebuild_dev(sysR.h, r_list, d_pos))
-        iters = 20
-        for _ in range(3):
-            capi.check(lib.ofly_eam_gradient_dev(sysR.h, d_outp))
-        ctx.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(iters):
-            capi.check(lib.ofly_eam_gradient_dev(sysR.h, d_outp))
-        g1.record(stream)
-        ctx.synchronize()
-        gms = g0.elapsed_time(g1) / iters
-        n2 = fly.List(sysR, 0).mean_count()
-        grad_leg = {"atom_evals_per_s": R * N / (gms * 1e-3), "ms_per_eval_batch": gms, "mean_neighbours": n2,
-                    "kernels": "k_eam_rho + k_eam_force (grid kernels, 64 x 16000 atoms per launch pair)"}
+    # the dominant kernels alone: gradient evaluations of the resident batch (every rank; rank 0 reports)
+    r_list = data.rcut() + 2 * ropt.delta_r
+    r_list += max(dopt.skin_frac ** (1 / 3) - 1, 0) * r_list
+    capi.check(lib.ofly_neigh_rebuild_dev(sysR.h, r_list, d_pos))
+    iters = 20
+    for _ in range(3):
+        capi.check(lib.ofly_eam_gradient_dev(sysR.h, d_outp))
+    ctx.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for _ in range(iters):
+        capi.check(lib.ofly_eam_gradient_dev(sysR.h, d_outp))
+    g1.record(stream)
+    ctx.synchronize()
+    gms = g0.elapsed_time(g1) / iters
+    n2 = fly.List(sysR, 0).mean_count()
+    grad_leg = {"atom_evals_per_s": R * N / (gms * 1e-3), "ms_per_launch_pair": gms, "mean_neighbours": n2, "launch_pairs_timed": iters}
 
     # reduce over ranks: max time, sum of work
     if world > 1:
@@ -230,31 +232,35 @@ def run_b200(args):
         value = evals_all * N * args.steps / sec
         e2e = evals_all * N * e2e_steps / e2e_s
         peak, peak_src = peaks()
-        b_alg = 8 * nbar + 64
-        # one launch of k_search = one step of this rank; per-rank algorithmic bytes / per-launch duration
-        achieved = (evals_step * N * b_alg) / (sec / args.steps) / 1e9
+        b_alg = 8 * grad_leg["mean_neighbours"] + 64
+        achieved = grad_leg["atom_evals_per_s"] * b_alg / 1e9
+        step_share = (evals_step * N / grad_leg["atom_evals_per_s"]) / (sec / args.steps)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "atoms": N, "replicas_per_gpu": R, "l2": "working set (neighbour rows 64x16000x~64x4 B + vectors) exceeds the 126 MB L2; no explicit flush",
+            "config": {"workload": WORKLOAD, "atoms": N, "replicas_per_gpu": R,
+                       "l2": "inputs larger than L2: neighbour rows 64x16000x104x4 B = 426 MB + 1.1 GB of search vectors vs 126 MB L2; no explicit flush",
                        "seed": args.seed},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * nbytes + rmin.nbytes),
                     "d2h_bytes_per_step": int(2 * nbytes + 4 * R + 32 * R), "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "ticks_per_step": ticks / args.steps,
+            "mean_active_replicas": evals_step / (ticks / args.steps),
             "dimer_searches_per_s": searches_all * args.steps / sec,
             "successful_saddles_per_s": success_all * args.steps / sec,
             "gradient_evals_per_search": evals_all / searches_all,
             "exit_codes": {str(k): int((code == k).sum()) for k in sorted(set(code.tolist()))},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_search (persistent, one launch per step)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_atom_eval": b_alg, "mean_neighbours": nbar,
-                         "note": "fp64 pipe co-limits this path (DESIGN.md); traffic from the ncu capture in profiles/"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC,
+                         "kernel": "k_eam_rho + k_eam_force: one EAM gradient evaluation of the resident batch (64 x 16000 atoms per launch pair)",
+                         "launch_ms": grad_leg["ms_per_launch_pair"], "launches_timed": grad_leg["launch_pairs_timed"],
+                         "peak_source": peak_src, "algorithmic_bytes_per_atom_eval": b_alg, "mean_neighbours": grad_leg["mean_neighbours"],
+                         "algorithmic_bytes_per_launch_pair": b_alg * R * N,
+                         "share_of_step_at_full_occupancy": step_share,
+                         "note": "bound in practice by the L1 data pipe (one wavefront per gathered 32 B sector), see DESIGN.md 4 and profiles/; "
+                                 "the search step as a whole moves %.1f GB/s of algorithmic gradient bytes" % (evals_step * N * b_alg / (sec / args.steps) / 1e9)},
             "clocks": clocks.summary(),
         }
-        if grad_leg:
-            grad_leg["roofline_frac"] = grad_leg["atom_evals_per_s"] * (8 * grad_leg["mean_neighbours"] + 64) / 1e9 / peak
-            out["gradient_kernel"] = grad_leg
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(rmin, ex, ids, P, A, steps=1)
         print(json.dumps(out), flush=True)

@@ -102,13 +102,26 @@ namespace ofly {
     RepState *state;  // [R]
     Control *ctl;
     int *active, *rebuild;  // [R] selection lists
+    int *flags;             // [R] per entry of `active`: bit 0 still active, bit 1 wants a rebuild (written by its team)
     int max_ticks;
     int use_cond;
+    unsigned long long *trace;  // tuning aid (OFLY_TRACE): [0] = count, then (mark, globaltimer ns) pairs of replica trace_replica
+    int trace_replica, trace_cap;
     int gram;  // 1: single-pass L-BFGS step (newton_step_gram), 0: pass-per-pair two-loop (newton_step)
     cudaGraphConditionalHandle cond;
     int use_cond_rebuild;  // the rebuild kernels of a tick sit in an IF node that is skipped when nobody asked
     cudaGraphConditionalHandle cond_rebuild;
   };
+
+  // Time stamp `mark` for the traced replica (thread 0 of its team only; off unless OFLY_TRACE is set).
+  __device__ __forceinline__ void trace_mark(const SearchParams &P, int r, int tid, int mark) {
+    if (P.trace != nullptr && tid == 0 && r == P.trace_replica) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      unsigned long long slot = atomicAdd(P.trace, 1ull);
+      if (slot < (unsigned long long)P.trace_cap) P.trace[1 + 2 * slot] = (unsigned long long)mark, P.trace[2 + 2 * slot] = t;
+    }
+  }
 
   // ---- team = one CTA or a cluster of C CTAs ------------------------------------------------------
   // Cluster-wide sums go through distributed shared memory without a cluster barrier: every CTA posts
@@ -157,6 +170,7 @@ namespace ofly {
     double out[kGramMax];        // team-wide sums, order index i (oldest pair first): {s_p.y_i, y_p.s_i, y_p.y_i, g.s_i, g.y_i}
     double alpha[kMaxHist], w[kMaxHist], h0;
     unsigned long long off[kMaxHist];  // element offset of pair i's row inside Core::s / Core::y
+    int slot[kMaxHist];                // ring-buffer slot of pair i
   };
 
   template <int C>
@@ -165,6 +179,11 @@ namespace ofly {
     double *red;    // shared: [2][C][kMaxRed] cluster slots, then [2][32][kMaxRed] warp partials
     uint64_t *bar;  // shared: [3] mbarriers: one per slot buffer, one for reduce_wide (clusters only)
     GramShared<C> *gram = nullptr;
+    const SearchParams *trace_params = nullptr;  // set per replica by the segment (tuning aid)
+    int trace_r = -1;
+    __device__ __forceinline__ void mark(int id) const {
+      if (trace_params) trace_mark(*trace_params, trace_r, tid, id);
+    }
     int parity = 0;
     uint32_t phase = 0;  // bit p: parity the next wait on bar[p] looks for
 
@@ -456,6 +475,7 @@ namespace ofly {
       });
     }
 
+    tm.mark(20);
     // pass A: every thread re-reads only its own elements of the newest pair
     for (int i0 = 0; i0 < bound; i0 += GS) {
       const double *sk[GS], *yk[GS];
@@ -508,7 +528,9 @@ namespace ofly {
         }
       }
     }
+    tm.mark(21);
     tm.reduce_wide(kGramVals * bound);
+    tm.mark(22);
 
     if (threadIdx.x == 0) {  // identical inputs, identical arithmetic on every CTA of the team
       const int p = prev;
@@ -517,35 +539,37 @@ namespace ofly {
         const double *v = G.out + kGramVals * i;
         G.sy[p * n + j] = v[0], G.sy[j * n + p] = v[1], G.yy[p * n + j] = v[2], G.yy[j * n + p] = v[2];
         G.off[i] = (unsigned long long)j * c.n3p;
+        G.slot[i] = j;
       }
       const double rho_p = 1.0 / fabs(G.sy[p * n + p]);  // abs: never an ascent direction (lbfgs_core.cpp:50)
       G.rho[p] = rho_p;
       const double h0 = 1.0 / rho_p / G.yy[p * n + p];   // initial Hessian scaling (lbfgs_core.cpp:70)
       G.h0 = h0;
       for (int i = bound - 1; i >= 0; --i) {  // loop 1, newest -> oldest
-        const int j = (i + incur) % n;
+        const int j = G.slot[i];
         double sq = G.out[kGramVals * i + 3];
-        for (int i2 = bound - 1; i2 > i; --i2) sq = fma(-G.alpha[i2], G.sy[j * n + (i2 + incur) % n], sq);
+        for (int i2 = bound - 1; i2 > i; --i2) sq = fma(-G.alpha[i2], G.sy[j * n + G.slot[i2]], sq);
         G.alpha[i] = G.rho[j] * sq;
       }
       for (int i = 0; i < bound; ++i) {  // loop 2, oldest -> newest
-        const int j = (i + incur) % n;
+        const int j = G.slot[i];
         double yq = G.out[kGramVals * i + 4];
-        for (int i2 = bound - 1; i2 >= 0; --i2) yq = fma(-G.alpha[i2], G.yy[j * n + (i2 + incur) % n], yq);
+        for (int i2 = bound - 1; i2 >= 0; --i2) yq = fma(-G.alpha[i2], G.yy[j * n + G.slot[i2]], yq);
         double yr = yq * h0;
-        for (int i2 = 0; i2 < i; ++i2) yr = fma(G.w[i2], G.sy[((i2 + incur) % n) * n + j], yr);
+        for (int i2 = 0; i2 < i; ++i2) yr = fma(G.w[i2], G.sy[G.slot[i2] * n + j], yr);
         G.w[i] = G.alpha[i] - G.rho[j] * yr;
       }
       if (tm.rank == 0) {  // persist the refreshed row / column
         c.st->rho[p] = rho_p;
         for (int i = 0; i < bound; i++) {
-          const int j = (i + incur) % n;
+          const int j = G.slot[i];
           c.st->sy[p * n + j] = G.sy[p * n + j], c.st->sy[j * n + p] = G.sy[j * n + p];
           c.st->yy[p * n + j] = G.yy[p * n + j], c.st->yy[j * n + p] = G.yy[j * n + p];
         }
       }
     }
     __syncthreads();
+    tm.mark(23);
 
     // pass B: step = (g - sum alpha_k y_k) h0 + sum w_k s_k, accumulated newest->oldest then oldest->newest
     const double h0 = G.h0;
@@ -576,7 +600,9 @@ namespace ofly {
       a[0] = fma(q, q, a[0]);
       if (w) a[1] = fma(q, wv, a[1]);
     }
+    tm.mark(24);
     tm.reduce<2>(a);
+    tm.mark(25);
     out_nrm2 = a[0], out_dotw = a[1];
     c.k++;
   }
@@ -617,7 +643,8 @@ namespace ofly {
     const BatchDev &B;
     const SearchParams &P;
     const int r, n3;
-    RepState *S;  // global
+    int entry = 0;  // position of this replica in the active list (where its fate is reported)
+    RepState *S;    // global
     Work W;
     // working copies of the persistent scalars
     int iter, rot_it, first, need_rebuild;
@@ -663,6 +690,7 @@ namespace ofly {
     __device__ void yield(int phase, double *dst) {
       if (tm.tid == 0) {
         S->phase = phase, S->iter = iter, S->rot_it = rot_it, S->first = first, S->need_rebuild = need_rebuild;
+        P.flags[entry] = 1 | (need_rebuild ? 2 : 0);
         S->gdst = (unsigned long long)(dst - W.base);
         S->trust = trust, S->acc = acc, S->convex_count = convex_count, S->curv = curv, S->mag_g = mag_g;
         S->c_x0 = c_x0, S->b_1 = b_1, S->theta_1 = theta_1;
@@ -687,6 +715,7 @@ namespace ofly {
           for (int q = 0; q < 4; q++) c[q] = tally[q];
         }
         S->phase = kDone, S->status = status, S->need_rebuild = 0;
+        P.flags[entry] = 0;
       }
     }
 
@@ -840,6 +869,7 @@ namespace ofly {
         }
       }
 
+      tm.mark(10);
       if (rot_head) {
         // torque: dg = (g1 - g0) - ((g1 - g0).axis) axis, minus its mean if nothing is frozen (rotor.cpp:89-94)
         double a7[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -864,8 +894,10 @@ namespace ofly {
         }
         __syncthreads();
 
+        tm.mark(11);
         double nrm2_unused, th_ax;
         lbfgs_step(W.rot, W.axis, W.dg, W.axis, nrm2_unused, th_ax);
+        tm.mark(12);
         double *theta = W.rot.step;
         // theta -= (theta.axis) axis ; normalise ; b_1 = (g1-g0).theta / dr   (rotor.cpp:99-103)
         double a2[2] = {0, 0};
@@ -902,10 +934,12 @@ namespace ofly {
             });
           }
           tally[2]++;
+          tm.mark(13);
           return yield(kRotG1p, W.g1p);
         }
       }
 
+      tm.mark(14);
       // ---- rotation finished: undo the end-point offset (rotor.cpp:150-151), effective gradient (:153-161)
       {
         double a7[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -969,9 +1003,12 @@ namespace ofly {
           if (ctheta > P.cos_theta_tol) return finish(-3);  // collision
         }
       }
+      tm.mark(15);
       double nrm2, unused;
       lbfgs_step(W.trans, W.x, W.g, (const double *)nullptr, nrm2, unused);
+      tm.mark(16);
       take_step(nrm2);
+      tm.mark(17);
       yield(kRotG0, W.g0);
     }
   };
@@ -988,30 +1025,44 @@ namespace ofly {
 
     Team<C> tm(red_smem, red_bar);
     tm.gram = &gram_smem;
-    const int r = blockIdx.x / C;
     const int n_teams = gridDim.x / C;
 
-    const int phase = P.state[r].phase;
-    if (phase != kDone) {
-      tm.init();
-      const int fault = __ldcg(B.fault + r);
-      Segment<C> seg(tm, B, P, r);
-      if (phase != kInit && (fault & kFaultCapacity)) {
-        seg.finish(kStatusCapacity);
-      } else if (phase != kInit && (fault & kFaultOutOfBounds)) {
-        seg.finish(kStatusOutOfBounds);  // the reference throws Spline::OutOfBounds out of find_sp / minimise
-      } else if (P.state[r].iter < 0) {
-        seg.finish(kStatusUnfinished);
-      } else {
-        if (phase == kInit && tm.tid == 0) B.fault[r] = 0;
-        if (P.mode == 0) {
-          seg.run_minimise(phase);
+    // Team t works through entries t, t + n_teams, ... of the list of replicas that were active after the
+    // previous tick (tick 0: all). Every CTA of a cluster takes the same branches, so the sequence of
+    // reductions -- which is what orders the shared-memory buffers between peers -- is the same on all of them.
+    const int n_listed = P.ctl->n_active;
+    tm.init();
+    for (int a = blockIdx.x / C; a < n_listed; a += n_teams) {
+      const int r = P.active[a];
+      const int phase = P.state[r].phase;
+      if (phase != kDone) {
+        const int fault = __ldcg(B.fault + r);
+        tm.trace_params = &P, tm.trace_r = r;
+        tm.mark(1);
+        Segment<C> seg(tm, B, P, r);
+        seg.entry = a;
+        tm.mark(2);
+        if (phase != kInit && (fault & kFaultCapacity)) {
+          seg.finish(kStatusCapacity);
+        } else if (phase != kInit && (fault & kFaultOutOfBounds)) {
+          seg.finish(kStatusOutOfBounds);  // the reference throws Spline::OutOfBounds out of find_sp / minimise
+        } else if (P.state[r].iter < 0) {
+          seg.finish(kStatusUnfinished);
         } else {
-          seg.run_dimer(phase);
+          if (phase == kInit && tm.tid == 0) B.fault[r] = 0;
+          if (P.mode == 0) {
+            seg.run_minimise(phase);
+          } else {
+            seg.run_dimer(phase);
+          }
         }
+      } else if (tm.tid == 0) {
+        P.flags[a] = 0;
       }
-      tm.fini();
+      tm.mark(90);
+      __syncthreads();  // the next replica reuses this CTA's shared buffers
     }
+    tm.fini();
 
     // The last team to arrive compiles the selection lists of this tick (in replica order, so the
     // grid kernels see a deterministic work order) and decides whether the graph body repeats.
@@ -1027,20 +1078,26 @@ namespace ofly {
         const int lane = threadIdx.x;
         const int tick = P.ctl->tick + 1;
         const bool out_of_ticks = tick >= P.max_ticks;
+        // Filter the old list in place (order preserved) with the flags its teams left; four independent loads
+        // per lane and sweep keep this serial tail short while thousands of replicas are listed.
         int na = 0, nr = 0;
-        for (int base = 0; base < B.R; base += 32) {
-          int q = base + lane;
-          bool act = false, reb = false;
-          if (q < B.R) {
-            volatile RepState *s = P.state + q;
-            act = s->phase != kDone;
-            reb = act && s->need_rebuild != 0;
-            if (act && out_of_ticks) s->iter = -1;  // flagged: finishes as kStatusUnfinished next tick
+        for (int base = 0; base < n_listed; base += 128) {
+          int q[4], f[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int a = base + 32 * u + lane;
+            q[u] = a < n_listed ? P.active[a] : 0;
+            f[u] = a < n_listed ? __ldcg(P.flags + a) : 0;
           }
-          unsigned ma = __ballot_sync(0xffffffffu, act), mr = __ballot_sync(0xffffffffu, reb);
-          if (act) P.active[na + __popc(ma & ((1u << lane) - 1u))] = q;
-          if (reb) P.rebuild[nr + __popc(mr & ((1u << lane) - 1u))] = q;
-          na += __popc(ma), nr += __popc(mr);
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const bool act = f[u] & 1, reb = (f[u] & 2) != 0;
+            if (act && out_of_ticks) P.state[q[u]].iter = -1;  // flagged: finishes as kStatusUnfinished next tick
+            unsigned ma = __ballot_sync(0xffffffffu, act), mr = __ballot_sync(0xffffffffu, reb);
+            if (act) P.active[na + __popc(ma & ((1u << lane) - 1u))] = q[u];
+            if (reb) P.rebuild[nr + __popc(mr & ((1u << lane) - 1u))] = q[u];
+            na += __popc(ma), nr += __popc(mr);
+          }
         }
         if (lane == 0) {
           P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;

@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <vector>
 #include <string>
 
 #include "internal.hpp"
@@ -46,12 +48,14 @@ namespace ofly {
       int threads, cluster;
     };
 
-    // Team of one replica's vector algebra: >= 16 elements per thread before the CTA is widened, then a
-    // cluster while every thread keeps >= 8 elements. The passes are latency-bound streams, and late in a
-    // batch only a few replicas are still active, so wide teams are what keeps bytes in flight.
+    // Team of one replica's vector algebra. The passes are latency-bound streams (a thread's elements are
+    // sequential round trips to L2/HBM) and for most ticks of a batch only a few replicas are still active, so
+    // the team is made as wide as the vector allows: >= 2 elements per thread up to a 512-thread CTA, then a
+    // cluster while every thread keeps >= 8 elements. The segment kernel strides over the list of active
+    // replicas, so wide teams cost extra sweeps only while many replicas are active (the first few % of ticks).
     TeamShape pick_team(ofly_ctx *, long, long n3) {
       TeamShape t{128, 1};
-      while (t.threads < kSegMaxThreads && n3 > (long)t.threads * 16) t.threads *= 2;
+      while (t.threads < kSegMaxThreads && n3 > (long)t.threads * 2) t.threads *= 2;
       if (t.threads == kSegMaxThreads) {
         while (t.cluster < 8 && n3 > (long)t.cluster * t.threads * 8) t.cluster *= 2;
       }
@@ -62,10 +66,11 @@ namespace ofly {
       return t;
     }
 
+    // Teams launched: one per replica up to what the chip holds at once (asked of the occupancy calculator:
+    // clusters are placed inside a GPC, so fewer fit than SMs / C); the kernel strides over the rest.
     template <int C, int MAXT>
-    void launch_segment(ofly_ctx *ctx, int teams, int threads, BatchDev const &B, SearchParams const &P) {
+    void launch_segment(ofly_ctx *ctx, ofly_batch *b, int threads, BatchDev const &B, SearchParams const &P) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(teams * C));
       cfg.blockDim = dim3((unsigned)threads);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = ctx->stream;
@@ -74,6 +79,20 @@ namespace ofly {
       attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = C > 1 ? 1 : 0;
+      long resident = 0;
+      if (C > 1) {
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / C * C));
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, k_segment<C, MAXT>, &cfg) != cudaSuccess) clusters = 0, cudaGetLastError();
+        resident = clusters;
+      } else {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_segment<C, MAXT>, threads, 0) != cudaSuccess) per_sm = 0, cudaGetLastError();
+        resident = (long)per_sm * ctx->sm_count;
+      }
+      if (resident <= 0) resident = std::max(1, ctx->sm_count / C);
+      const long teams = std::min<long>(b->R, resident);
+      cfg.gridDim = dim3((unsigned)(teams * C));
       OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT>, B, P));
     }
 
@@ -86,22 +105,21 @@ namespace ofly {
     void enqueue_segment(ofly_batch *b, SearchParams const &P, TeamShape shape) {
       ofly_ctx *ctx = b->ctx;
       BatchDev const &B = b->d;
-      const int teams = (int)b->R;
       switch (shape.cluster) {
         case 8:
-          launch_segment<8, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
+          launch_segment<8, kSegMaxThreads>(ctx, b, shape.threads, B, P);
           break;
         case 4:
-          launch_segment<4, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
+          launch_segment<4, kSegMaxThreads>(ctx, b, shape.threads, B, P);
           break;
         case 2:
-          launch_segment<2, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
+          launch_segment<2, kSegMaxThreads>(ctx, b, shape.threads, B, P);
           break;
         default:
           if (shape.threads <= 128) {
-            launch_segment<1, 128>(ctx, teams, shape.threads, B, P);
+            launch_segment<1, 128>(ctx, b, shape.threads, B, P);
           } else {
-            launch_segment<1, kSegMaxThreads>(ctx, teams, shape.threads, B, P);
+            launch_segment<1, kSegMaxThreads>(ctx, b, shape.threads, B, P);
           }
           break;
       }
@@ -323,15 +341,16 @@ namespace ofly {
       const TeamShape shape = pick_team(ctx, b->R, 3 * b->N);
       P.ws_stride = search_ws_doubles(P.mode, P.n_hist, P.rot_n, n3p);
 
-      // arena: control block | replica states | two selection lists | vectors
+      // arena: control block | replica states | two selection lists + entry flags | vectors
       static_assert(sizeof(RepState) % 8 == 0 && sizeof(Control) % 8 == 0, "layout");
-      const size_t head = 256 + ((R * sizeof(RepState) + 2 * R * sizeof(int) + 255) & ~(size_t)255);
+      const size_t head = 256 + ((R * sizeof(RepState) + 3 * R * sizeof(int) + 255) & ~(size_t)255);
       b->search_ws.reserve(head + P.ws_stride * R * sizeof(double));
       char *base = b->search_ws.p;
       P.ctl = reinterpret_cast<Control *>(base);
       P.state = reinterpret_cast<RepState *>(base + 256);
       P.active = reinterpret_cast<int *>(base + 256 + R * sizeof(RepState));
       P.rebuild = P.active + R;
+      P.flags = P.rebuild + R;
       P.ws = reinterpret_cast<double *>(base + head);
       P.pos_in = io.pos_in, P.axis_in = io.axis_in, P.in_min = io.in_min, P.hist_sp = io.hist_sp;
       P.pos_out = io.pos_out, P.axis_out = io.axis_out, P.grad_out = io.grad_out, P.status = io.status, P.counters = io.counters;
@@ -350,8 +369,43 @@ namespace ofly {
         return !(v && std::string(v) == "host");
       }();
 
+      // OFLY_TRACE=<replica>: time stamps inside the segment kernel for that replica, summarised on stderr.
+      DevBuf<unsigned long long> trace;
+      const int trace_cap = 1 << 19;
+      if (char const *tv = std::getenv("OFLY_TRACE")) {
+        trace.reserve(1 + 2 * (size_t)trace_cap);
+        OFLY_CUDA(cudaMemsetAsync(trace.p, 0, 8, ctx->stream));
+        P.trace = trace.p, P.trace_replica = std::atoi(tv), P.trace_cap = trace_cap;
+      }
+      struct TraceDump {
+        DevBuf<unsigned long long> &t;
+        int cap;
+        ~TraceDump() {
+          if (!t.p) return;
+          std::vector<unsigned long long> h(1 + 2 * (size_t)cap);
+          if (cudaMemcpy(h.data(), t.p, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            size_t n = std::min<size_t>(h[0], (size_t)cap);
+            std::map<std::pair<int, int>, std::pair<double, long>> acc;
+            for (size_t k = 1; k < n; k++) {
+              int a = (int)h[1 + 2 * (k - 1)], b = (int)h[1 + 2 * k];
+              double dt = (double)(h[2 + 2 * k] - h[2 + 2 * (k - 1)]);
+              auto &e = acc[{a, b}];
+              e.first += dt, e.second++;
+            }
+            std::fprintf(stderr, "openfly_b200 trace: %zu marks\n", n);
+            for (auto const &kv : acc)
+              std::fprintf(stderr, "  %2d -> %2d : n=%7ld mean %9.1f ns total %9.3f ms\n", kv.first.first, kv.first.second, kv.second.second,
+                           kv.second.first / kv.second.second, kv.second.first * 1e-6);
+          }
+          t.release();
+        }
+      } trace_dump{trace, trace_cap};
+
       for (int attempt = 0;; attempt++) {
         OFLY_CUDA(cudaMemsetAsync(base, 0, head, ctx->stream));
+        // tick 0: every replica is active (sel_all = 0..R-1 followed by R)
+        OFLY_CUDA(cudaMemcpyAsync(P.active, b->sel_all.p, R * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        OFLY_CUDA(cudaMemcpyAsync(&P.ctl->n_active, b->sel_all.p + R, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         if (device_loop) {
           run_device_loop(b, P, shape);
         } else {

@@ -24,3 +24,7 @@ for _ in range(rep):
     ev = cnt[:, 0].sum()
     print(f"dimer R={R} N={len(ids)}: {dt*1e3:.1f} ms, ticks {ticks:.0f} ({dt/ticks*1e6:.1f} us/tick), evals {ev} max {cnt[:,0].max()}, "
           f"{ev*len(ids)/dt:.3e} atom-evals/s, exits {dict(zip(*np.unique(code, return_counts=True)))}")
+if os.environ.get("OFLY_TRACE_LONGEST"):
+    os.environ["OFLY_TRACE"] = str(int(np.argmax(cnt[:, 0])))
+    print("tracing replica", os.environ["OFLY_TRACE"], "evals", cnt[:, 0].max(), flush=True)
+    fly.Dimer().find_sp(sR, P, A, rmin[0], pot)
