@@ -131,7 +131,7 @@ namespace ofly {
 
   // Pass 1: rho and F'(rho) -> pos4[].w
   template <int G>
-  static __global__ void __launch_bounds__(256) k_eam_rho(BatchDev B, TablesDev T, Sel S) {
+  __device__ __forceinline__ void eam_rho_tiles(const BatchDev &B, const TablesDev &T, const Sel &S) {
     constexpr int kTile = 256 / G;
     const int tiles = (B.N + kTile - 1) / kTile;
     const long items = (long)(*S.count) * tiles;
@@ -149,12 +149,16 @@ namespace ofly {
       if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
   }
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_eam_rho(BatchDev B, TablesDev T, Sel S) {
+    eam_rho_tiles<G>(B, T, S);
+  }
 
   // Pass 2: gradient of replica r -> out + r * stride + offset[r * offset_stride] (offset may be null).
   // The search keeps, per replica, the slot its next gradient belongs in (g0, g1, g1' of the rotor).
   template <int G>
-  static __global__ void __launch_bounds__(256) k_eam_force(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
-                                                            const unsigned long long *__restrict__ offset, size_t offset_stride) {
+  __device__ __forceinline__ void eam_force_tiles(const BatchDev &B, const TablesDev &T, const Sel &S, double *__restrict__ out, size_t stride,
+                                                  const unsigned long long *__restrict__ offset, size_t offset_stride) {
     constexpr int kTile = 256 / G;
     const int tiles = (B.N + kTile - 1) / kTile;
     const long items = (long)(*S.count) * tiles;
@@ -171,6 +175,43 @@ namespace ofly {
         o[0] = gx, o[1] = gy, o[2] = gz;
       }
       if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
+    }
+  }
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_eam_force(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
+                                                            const unsigned long long *__restrict__ offset, size_t offset_stride) {
+    eam_force_tiles<G>(B, T, S, out, stride, offset, offset_stride);
+  }
+
+  // Sub-warp width for `atoms` atoms of work on a chip with `slots` resident threads: few atoms -> wide groups
+  // (more threads, shorter per-lane chains: latency), many atoms -> narrow groups (fewer idle lanes on the ragged
+  // row tail: throughput).
+  __host__ __device__ inline int group_for(long atoms, long slots) {
+    if (atoms * 4 >= 2 * slots) return 4;
+    if (atoms * 8 >= 2 * slots) return 8;
+    if (atoms * 16 >= slots) return 16;
+    return 32;
+  }
+
+  // The search's tick kernels pick G on the device from the number of replicas still active: for most ticks of
+  // a batch only a few replicas are left and the evaluation is a latency chain, not a throughput problem.
+  // (The lane count sets the order of the per-atom sum, so a replica's rounding depends on how many replicas are
+  // active with it: deterministic for a given batch, not identical across batch compositions.)
+  static __global__ void __launch_bounds__(256) k_eam_rho_dyn(BatchDev B, TablesDev T, Sel S, long slots) {
+    switch (group_for((long)(*S.count) * B.N, slots)) {
+      case 4: eam_rho_tiles<4>(B, T, S); break;
+      case 8: eam_rho_tiles<8>(B, T, S); break;
+      case 16: eam_rho_tiles<16>(B, T, S); break;
+      default: eam_rho_tiles<32>(B, T, S); break;
+    }
+  }
+  static __global__ void __launch_bounds__(256) k_eam_force_dyn(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
+                                                                const unsigned long long *__restrict__ offset, size_t offset_stride, long slots) {
+    switch (group_for((long)(*S.count) * B.N, slots)) {
+      case 4: eam_force_tiles<4>(B, T, S, out, stride, offset, offset_stride); break;
+      case 8: eam_force_tiles<8>(B, T, S, out, stride, offset, offset_stride); break;
+      case 16: eam_force_tiles<16>(B, T, S, out, stride, offset, offset_stride); break;
+      default: eam_force_tiles<32>(B, T, S, out, stride, offset, offset_stride); break;
     }
   }
 

@@ -254,7 +254,7 @@ namespace ofly {
 
   // One work item = one tile of 256/G consecutive atoms of one selected replica.
   template <int G>
-  static __global__ void __launch_bounds__(256) k_nb_build(BatchDev B, Sel S) {
+  __device__ __forceinline__ void nb_build_tiles(const BatchDev &B, const Sel &S) {
     constexpr int kTile = 256 / G;
     const int tiles = (B.N + kTile - 1) / kTile;
     const long items = (long)(*S.count) * tiles;
@@ -263,6 +263,24 @@ namespace ofly {
       int r = S.list[w / tiles];
       int i = (int)(w % tiles) * kTile + threadIdx.x / G;
       if (i < B.N) nb_build_atom<G>(B, r, i, lane);  // whole sub-warps are in or out together
+    }
+  }
+  template <int G>
+  static __global__ void __launch_bounds__(256) k_nb_build(BatchDev B, Sel S) {
+    nb_build_tiles<G>(B, S);
+  }
+  // Sub-warp width picked on the device from the number of selected replicas (the stored row is a compaction in
+  // candidate order, so the list does not depend on G).
+  static __global__ void __launch_bounds__(256) k_nb_build_dyn(BatchDev B, Sel S, long slots) {
+    const long atoms = (long)(*S.count) * B.N;
+    if (atoms * 4 >= 2 * slots) {
+      nb_build_tiles<4>(B, S);
+    } else if (atoms * 8 >= 2 * slots) {
+      nb_build_tiles<8>(B, S);
+    } else if (atoms * 16 >= slots) {
+      nb_build_tiles<16>(B, S);
+    } else {
+      nb_build_tiles<32>(B, S);
     }
   }
 

@@ -434,6 +434,56 @@ namespace ofly {
     c.k++;
   }
 
+  // The rotor's torque as an on-the-fly gradient for newton_step_gram: g = (g1 - g0) - pax x - mean[component].
+  struct TorqueGen {
+    const double *g1, *g0;
+    double pax, mean[3];
+  };
+
+  // Pass B of newton_step_gram for up to MAXB stored pairs. MAXB = 8 (the rotor's n = 6): the y and s rows of an
+  // element are all requested together, one round trip per element; MAXB = 16: y rows, then s rows (registers).
+  template <int C, int MAXB>
+  __device__ __forceinline__ void gram_combine(const GramShared<C> &G, const Core &c, const double *g, const double *w, int n3, int tid, int nth,
+                                               int bound, double h0, double (&a)[2]) {
+    double *out = c.step;
+    for (int t = tid; t < n3; t += nth) {
+      double h[MAXB], hs[MAXB <= 8 ? MAXB : 1];
+#pragma unroll
+      for (int i = 0; i < MAXB; i++) {
+        if (i < bound) {
+          h[i] = c.y[G.off[i] + t];
+          if constexpr (MAXB <= 8) hs[i] = c.s[G.off[i] + t];
+        }
+      }
+      double q = g[t];
+      const double wv = w ? w[t] : 0.0;
+#pragma unroll
+      for (int i = MAXB - 1; i >= 0; --i) {
+        if (i < bound) q = fma(-G.alpha[i], h[i], q);
+      }
+      q *= h0;
+      if constexpr (MAXB > 8) {
+#pragma unroll
+        for (int i = 0; i < MAXB; i++) {
+          if (i < bound) h[i] = c.s[G.off[i] + t];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MAXB; i++) {
+        if (i < bound) {
+          if constexpr (MAXB <= 8) {
+            q = fma(G.w[i], hs[i], q);
+          } else {
+            q = fma(G.w[i], h[i], q);
+          }
+        }
+      }
+      out[t] = q;
+      a[0] = fma(q, q, a[0]);
+      if (w) a[1] = fma(q, wv, a[1]);
+    }
+  }
+
   // StepLBFGS::newton_step in TWO streaming passes instead of one pass per history pair.
   //
   // The two-loop recursion only ever needs the running vector q through its dot products with the stored
@@ -449,8 +499,8 @@ namespace ofly {
   // bound by exactly that chain once few replicas are left -- for the same bytes streamed.
   // Differs from the two-loop only in how alpha/beta are rounded (scripts/lbfgs_gram_study.py).
   template <int C>
-  __device__ __forceinline__ void newton_step_gram(Team<C> &tm, Core &c, const double *x, const double *g, int n3, const double *w,
-                                                double &out_nrm2, double &out_dotw) {
+  __device__ __forceinline__ void newton_step_gram(Team<C> &tm, Core &c, const double *x, double *g, int n3, const double *w,
+                                                double &out_nrm2, double &out_dotw, const TorqueGen *tg = nullptr) {
     if (c.k == 0) return newton_step(tm, c, x, g, n3, w, out_nrm2, out_dotw);  // identity Hessian: one pass
 
     constexpr int GS = 3;  // pairs per sweep of pass A (5 accumulators each)
@@ -468,10 +518,19 @@ namespace ofly {
     for (int t = threadIdx.x; t < n * n; t += blockDim.x) G.sy[t] = c.st->sy[t], G.yy[t] = c.st->yy[t];
     if (threadIdx.x < n) G.rho[threadIdx.x] = c.st->rho[threadIdx.x];
 
-    {  // newest pair (s, y); prev <- current   (lbfgs_core.cpp:37-52)
+    if (tg == nullptr) {  // newest pair (s, y); prev <- current   (lbfgs_core.cpp:37-52)
       const double *const src[4] = {x, g, c.prev_x, c.prev_g};
       team_pass<4>(tid, nth, n3, src, [&](int t, const double(&v)[4]) {
         sp[t] = v[0] - v[2], yp[t] = v[1] - v[3], c.prev_x[t] = v[0], c.prev_g[t] = v[1];
+      });
+    } else {  // the same with g = the rotor's torque formed on the fly from g1, g0 and x = axis (rotor.cpp:89-94)
+      const double pax = tg->pax, m0 = tg->mean[0], m1 = tg->mean[1], m2 = tg->mean[2];
+      const double *const src[5] = {x, tg->g1, tg->g0, c.prev_x, c.prev_g};
+      team_pass<5>(tid, nth, n3, src, [&](int t, const double(&v)[5]) {
+        const int cmp = t % 3;
+        const double gv = (v[1] - v[2]) - pax * v[0] - (cmp == 0 ? m0 : (cmp == 1 ? m1 : m2));
+        g[t] = gv;
+        sp[t] = v[0] - v[3], yp[t] = gv - v[4], c.prev_x[t] = v[0], c.prev_g[t] = gv;
       });
     }
 
@@ -532,39 +591,54 @@ namespace ofly {
     tm.reduce_wide(kGramVals * bound);
     tm.mark(22);
 
-    if (threadIdx.x == 0) {  // identical inputs, identical arithmetic on every CTA of the team
+    // Scalar recursion by warp 0 (identical inputs, identical arithmetic on every CTA of the team). Lane i owns
+    // pair i (order index, oldest first) with its Gram rows in registers; both triangular sweeps broadcast one
+    // coefficient per step, so the dependent chain is ~n shuffles + FMAs instead of ~n^2 shared-memory round trips.
+    // Each lane accumulates in the order the serial recursion would.
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
       const int p = prev;
-      for (int i = 0; i < bound; i++) {
-        const int j = (i + incur) % n;
-        const double *v = G.out + kGramVals * i;
+      const bool mine = lane < bound;
+      const int j = mine ? (lane + incur) % n : 0;
+      const double *v = G.out + kGramVals * (mine ? lane : 0);
+      if (mine) {  // refresh row / column p with this step's sums (entry (p, p) is written twice with the same bits)
         G.sy[p * n + j] = v[0], G.sy[j * n + p] = v[1], G.yy[p * n + j] = v[2], G.yy[j * n + p] = v[2];
-        G.off[i] = (unsigned long long)j * c.n3p;
-        G.slot[i] = j;
+        G.off[lane] = (unsigned long long)j * c.n3p;
+        G.slot[lane] = j;
       }
+      __syncwarp();
       const double rho_p = 1.0 / fabs(G.sy[p * n + p]);  // abs: never an ascent direction (lbfgs_core.cpp:50)
-      G.rho[p] = rho_p;
       const double h0 = 1.0 / rho_p / G.yy[p * n + p];   // initial Hessian scaling (lbfgs_core.cpp:70)
-      G.h0 = h0;
-      for (int i = bound - 1; i >= 0; --i) {  // loop 1, newest -> oldest
-        const int j = G.slot[i];
-        double sq = G.out[kGramVals * i + 3];
-        for (int i2 = bound - 1; i2 > i; --i2) sq = fma(-G.alpha[i2], G.sy[j * n + G.slot[i2]], sq);
-        G.alpha[i] = G.rho[j] * sq;
+      const double rho_i = !mine ? 0.0 : (j == p ? rho_p : G.rho[j]);
+      const double *sy_row = G.sy + j * n, *yy_row = G.yy + j * n;  // s_i.y_k and y_i.y_k at column slot(k)
+      // loop 1, newest -> oldest: alpha_i = rho_i (s_i.g - sum_{k newer} alpha_k s_i.y_k)
+      double sq = v[3], alpha_i = 0.0;
+      double yq = v[4];  // y_i.g - sum_k alpha_k y_i.y_k, k newest -> oldest (enters loop 2)
+#pragma unroll 1
+      for (int k = bound - 1; k >= 0; --k) {
+        const int jk = G.slot[k];
+        const double s_iyk = sy_row[jk], y_iyk = yy_row[jk];
+        const double alpha_k = __shfl_sync(0xffffffffu, rho_i * sq, k);
+        if (lane == k) alpha_i = alpha_k;
+        if (lane < k) sq = fma(-alpha_k, s_iyk, sq);
+        yq = fma(-alpha_k, y_iyk, yq);
       }
-      for (int i = 0; i < bound; ++i) {  // loop 2, oldest -> newest
-        const int j = G.slot[i];
-        double yq = G.out[kGramVals * i + 4];
-        for (int i2 = bound - 1; i2 >= 0; --i2) yq = fma(-G.alpha[i2], G.yy[j * n + G.slot[i2]], yq);
-        double yr = yq * h0;
-        for (int i2 = 0; i2 < i; ++i2) yr = fma(G.w[i2], G.sy[G.slot[i2] * n + j], yr);
-        G.w[i] = G.alpha[i] - G.rho[j] * yr;
+      // loop 2, oldest -> newest: w_i = alpha_i - rho_i (h0 yq_i + sum_{k older} w_k s_k.y_i)
+      double yr = yq * h0, w_i = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < bound; k++) {
+        const double s_kyi = G.sy[G.slot[k] * n + j];
+        const double w_k = __shfl_sync(0xffffffffu, alpha_i - rho_i * yr, k);
+        if (lane == k) w_i = w_k;
+        if (lane > k) yr = fma(w_k, s_kyi, yr);
       }
+      if (mine) G.alpha[lane] = alpha_i, G.w[lane] = w_i;
+      if (lane == 0) G.h0 = h0;
       if (tm.rank == 0) {  // persist the refreshed row / column
-        c.st->rho[p] = rho_p;
-        for (int i = 0; i < bound; i++) {
-          const int j = G.slot[i];
-          c.st->sy[p * n + j] = G.sy[p * n + j], c.st->sy[j * n + p] = G.sy[j * n + p];
-          c.st->yy[p * n + j] = G.yy[p * n + j], c.st->yy[j * n + p] = G.yy[j * n + p];
+        if (lane == 0) c.st->rho[p] = rho_p;
+        if (mine) {
+          c.st->sy[p * n + j] = v[0], c.st->sy[j * n + p] = v[1];
+          c.st->yy[p * n + j] = v[2], c.st->yy[j * n + p] = v[2];
         }
       }
     }
@@ -573,32 +647,11 @@ namespace ofly {
 
     // pass B: step = (g - sum alpha_k y_k) h0 + sum w_k s_k, accumulated newest->oldest then oldest->newest
     const double h0 = G.h0;
-    double *out = c.step;
     double a[2] = {0, 0};
-    for (int t = tid; t < n3; t += nth) {
-      double h[kMaxHist];
-#pragma unroll
-      for (int i = 0; i < kMaxHist; i++) {
-        if (i < bound) h[i] = c.y[G.off[i] + t];
-      }
-      double q = g[t];
-      const double wv = w ? w[t] : 0.0;
-#pragma unroll
-      for (int i = kMaxHist - 1; i >= 0; --i) {
-        if (i < bound) q = fma(-G.alpha[i], h[i], q);
-      }
-      q *= h0;
-#pragma unroll
-      for (int i = 0; i < kMaxHist; i++) {
-        if (i < bound) h[i] = c.s[G.off[i] + t];
-      }
-#pragma unroll
-      for (int i = 0; i < kMaxHist; i++) {
-        if (i < bound) q = fma(G.w[i], h[i], q);
-      }
-      out[t] = q;
-      a[0] = fma(q, q, a[0]);
-      if (w) a[1] = fma(q, wv, a[1]);
+    if (bound <= 8) {
+      gram_combine<C, 8>(G, c, g, w, n3, tid, nth, bound, h0, a);
+    } else {
+      gram_combine<C, kMaxHist>(G, c, g, w, n3, tid, nth, bound, h0, a);
     }
     tm.mark(24);
     tm.reduce<2>(a);
@@ -681,13 +734,14 @@ namespace ofly {
     // what it wrote itself: inside a segment no global data crosses threads.
     static __device__ __forceinline__ int pos_slot(int t) { return t + t / 3; }
 
-    __device__ __forceinline__ void lbfgs_step(Core &c, const double *x, const double *g, const double *w, double &nrm2, double &dotw) {
-      if (P.gram) return newton_step_gram<C>(tm, c, x, g, n3, w, nrm2, dotw);
+    __device__ __forceinline__ void lbfgs_step(Core &c, const double *x, double *g, const double *w, double &nrm2, double &dotw,
+                                               const TorqueGen *tg = nullptr) {
+      if (P.gram) return newton_step_gram<C>(tm, c, x, g, n3, w, nrm2, dotw, tg);
       newton_step(tm, c, x, g, n3, w, nrm2, dotw);
     }
 
     // Suspend until the gradient of the current list positions is in `dst`; resume at `phase`.
-    __device__ void yield(int phase, double *dst) {
+    __device__ __forceinline__ void yield(int phase, double *dst) {
       if (tm.tid == 0) {
         S->phase = phase, S->iter = iter, S->rot_it = rot_it, S->first = first, S->need_rebuild = need_rebuild;
         P.flags[entry] = 1 | (need_rebuild ? 2 : 0);
@@ -701,7 +755,7 @@ namespace ofly {
     }
 
     // Write the results of a finished replica.
-    __device__ void finish(int status) {
+    __device__ __forceinline__ void finish(int status) {
       __syncthreads();
       for (int t = tm.tid; t < n3; t += tm.nthreads) {
         P.pos_out[(size_t)r * n3 + t] = W.x[t];
@@ -721,7 +775,7 @@ namespace ofly {
 
     // neigh::List::rebuild(x) request: the grid kernels of this tick do the work; the histogram of
     // the replica must be zero before they start.
-    __device__ void request_rebuild() {
+    __device__ __forceinline__ void request_rebuild() {
       int *hist = B.cell_count + (size_t)r * B.grid.ncells;
       for (int c = tm.tid; c < B.grid.ncells; c += tm.nthreads) hist[c] = 0;
       need_rebuild = 1;
@@ -730,7 +784,7 @@ namespace ofly {
 
     // Trust-limited step shared by the minimiser and the dimer (lbfgs.cpp:83-100, dimer.cpp:133-151):
     // Hg *= min(1, trust/|Hg|); acc += |Hg|; x -= Hg; then rebuild if acc > skin/2 else update(Hg).
-    __device__ void take_step(double nrm2) {
+    __device__ __forceinline__ void take_step(double nrm2) {
       const double nrm = sqrt(nrm2);
       const double scale = fmin(1.0, trust / nrm);
       acc += scale * nrm;
@@ -755,7 +809,7 @@ namespace ofly {
     }
 
     // ---- minimise::LBFGS::minimise ----------------------------------------------------------------
-    __device__ void run_minimise(int phase) {
+    __device__ __forceinline__ void run_minimise(int phase) {
       if (phase == kInit) {
         for (int t = tm.tid; t < n3; t += tm.nthreads) W.x[t] = P.pos_in[(size_t)r * n3 + t];
         W.trans.k = 0;
@@ -794,7 +848,7 @@ namespace ofly {
 
     // ---- saddle::Rotor::eff_gradient + saddle::Dimer::find_sp ---------------------------------------
     // Returns true if the replica finished or suspended; false never.
-    __device__ void run_dimer(int phase) {
+    __device__ __forceinline__ void run_dimer(int phase) {
       const double dr = P.delta_r;
       const double inv_n = 1.0 / (double)B.N;
       double *p4 = reinterpret_cast<double *>(pos());
@@ -811,7 +865,8 @@ namespace ofly {
         return yield(kRotG0, W.g0);  // eff_gradient starts with pot.gradient(g0) (rotor.cpp:75)
       }
 
-      bool rot_head = false;
+      bool rot_head = false, have_torque = false;
+      double a7[7] = {0, 0, 0, 0, 0, 0, 0};  // (g1-g0).axis, sum(g1-g0)[3], sum(axis)[3]
       if (phase == kRotG0) {
         // delta = -dr * axis ; nl.update(delta) ; delta_prev = delta ; gradient(g1)   (rotor.cpp:77-85)
         tally[0]++;
@@ -847,7 +902,8 @@ namespace ofly {
 
         const double cm = cos(theta_min), sm = sin(theta_min);
         const double k1 = sin(theta_1 - theta_min) / s1, k2 = sm / s1, k3 = 1 - cm - sm * tan(0.5 * theta_1);
-        double ac[1] = {0};
+        // The same pass accumulates what the next rotation iteration's torque needs ((g1-g0).axis and the component
+        // sums of g1-g0 and axis), element by element exactly as the separate pass below would.
         {
           const double *const src[5] = {W.axis, theta, W.g0, W.g1, W.g1p};
           team_pass<5>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[5]) {
@@ -856,24 +912,26 @@ namespace ofly {
             double g0v = v[2];
             double gn = k1 * v[3] + k2 * v[4] + k3 * g0v;  // interpolated end-point gradient (rotor.cpp:132-134)
             W.g1[t] = gn;
-            ac[0] = fma(gn - g0v, an, ac[0]);
+            double dv = gn - g0v;
+            a7[0] = fma(dv, an, a7[0]);
+            int c = t % 3;
+            a7[1 + c] += dv, a7[4 + c] += an;
           });
         }
+        tm.reduce<7>(a7);
         if (fabs(theta_min) < P.rot_theta_tol) {
-          tm.reduce<1>(ac);
-          curv = ac[0] / dr;
+          curv = a7[0] / dr;
         } else {
-          __syncthreads();
           rot_it++;
           rot_head = true;
+          have_torque = true;
         }
       }
 
       tm.mark(10);
       if (rot_head) {
         // torque: dg = (g1 - g0) - ((g1 - g0).axis) axis, minus its mean if nothing is frozen (rotor.cpp:89-94)
-        double a7[7] = {0, 0, 0, 0, 0, 0, 0};
-        {
+        if (!have_torque) {
           const double *const src[3] = {W.g1, W.g0, W.axis};
           team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
             double dv = v[0] - v[1], av = v[2];
@@ -881,22 +939,24 @@ namespace ofly {
             int c = t % 3;
             a7[1 + c] += dv, a7[4 + c] += av;
           });
+          tm.reduce<7>(a7);
         }
-        tm.reduce<7>(a7);
         const double pax = a7[0];
-        double mean[3] = {0, 0, 0};
+        TorqueGen tg{W.g1, W.g0, pax, {0, 0, 0}};
         if (P.count_frozen == 0) {
-          for (int c = 0; c < 3; c++) mean[c] = (a7[1 + c] - pax * a7[4 + c]) * inv_n;
+          for (int c = 0; c < 3; c++) tg.mean[c] = (a7[1 + c] - pax * a7[4 + c]) * inv_n;
         }
-        {
+        // With stored pairs the single-pass step forms dg inside its first pass; otherwise it is written here.
+        const bool fused = P.gram && W.rot.k > 0;
+        if (!fused) {
           const double *const src[3] = {W.g1, W.g0, W.axis};
-          team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) { W.dg[t] = (v[0] - v[1]) - pax * v[2] - mean[t % 3]; });
+          team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) { W.dg[t] = (v[0] - v[1]) - pax * v[2] - tg.mean[t % 3]; });
+          __syncthreads();
         }
-        __syncthreads();
 
         tm.mark(11);
         double nrm2_unused, th_ax;
-        lbfgs_step(W.rot, W.axis, W.dg, W.axis, nrm2_unused, th_ax);
+        lbfgs_step(W.rot, W.axis, W.dg, W.axis, nrm2_unused, th_ax, fused ? &tg : nullptr);
         tm.mark(12);
         double *theta = W.rot.step;
         // theta -= (theta.axis) axis ; normalise ; b_1 = (g1-g0).theta / dr   (rotor.cpp:99-103)
@@ -1025,17 +1085,17 @@ namespace ofly {
 
     Team<C> tm(red_smem, red_bar);
     tm.gram = &gram_smem;
-    const int n_teams = gridDim.x / C;
-
-    // Team t works through entries t, t + n_teams, ... of the list of replicas that were active after the
-    // previous tick (tick 0: all). Every CTA of a cluster takes the same branches, so the sequence of
-    // reductions -- which is what orders the shared-memory buffers between peers -- is the same on all of them.
+    // Team t owns entry t of the list of replicas that were active after the previous tick (tick 0: all); the
+    // teams beyond the list leave at once. (A loop over entries inside the kernel would let the compiler hoist
+    // every loop-invariant address out of it and spill them all.)
     const int n_listed = P.ctl->n_active;
-    tm.init();
-    for (int a = blockIdx.x / C; a < n_listed; a += n_teams) {
+    const int a = blockIdx.x / C;
+    if (a >= n_listed) return;  // whole clusters leave together
+    {
       const int r = P.active[a];
       const int phase = P.state[r].phase;
       if (phase != kDone) {
+        tm.init();
         const int fault = __ldcg(B.fault + r);
         tm.trace_params = &P, tm.trace_r = r;
         tm.mark(1);
@@ -1056,13 +1116,12 @@ namespace ofly {
             seg.run_dimer(phase);
           }
         }
+        tm.mark(90);
+        tm.fini();
       } else if (tm.tid == 0) {
         P.flags[a] = 0;
       }
-      tm.mark(90);
-      __syncthreads();  // the next replica reuses this CTA's shared buffers
     }
-    tm.fini();
 
     // The last team to arrive compiles the selection lists of this tick (in replica order, so the
     // grid kernels see a deterministic work order) and decides whether the graph body repeats.
@@ -1070,7 +1129,7 @@ namespace ofly {
       __syncthreads();
       if (threadIdx.x == 0) {
         __threadfence();
-        last_team = atomicAdd(&P.ctl->ticket, 1) == n_teams - 1;
+        last_team = atomicAdd(&P.ctl->ticket, 1) == n_listed - 1;
       }
       __syncthreads();
       if (last_team && threadIdx.x < 32) {

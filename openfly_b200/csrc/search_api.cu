@@ -66,11 +66,11 @@ namespace ofly {
       return t;
     }
 
-    // Teams launched: one per replica up to what the chip holds at once (asked of the occupancy calculator:
-    // clusters are placed inside a GPC, so fewer fit than SMs / C); the kernel strides over the rest.
+    // One team per replica slot; the teams beyond the list of active replicas leave at once.
     template <int C, int MAXT>
     void launch_segment(ofly_ctx *ctx, ofly_batch *b, int threads, BatchDev const &B, SearchParams const &P) {
       cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(b->R * C));
       cfg.blockDim = dim3((unsigned)threads);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = ctx->stream;
@@ -79,20 +79,6 @@ namespace ofly {
       attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = C > 1 ? 1 : 0;
-      long resident = 0;
-      if (C > 1) {
-        cfg.gridDim = dim3((unsigned)(ctx->sm_count / C * C));
-        int clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&clusters, k_segment<C, MAXT>, &cfg) != cudaSuccess) clusters = 0, cudaGetLastError();
-        resident = clusters;
-      } else {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_segment<C, MAXT>, threads, 0) != cudaSuccess) per_sm = 0, cudaGetLastError();
-        resident = (long)per_sm * ctx->sm_count;
-      }
-      if (resident <= 0) resident = std::max(1, ctx->sm_count / C);
-      const long teams = std::min<long>(b->R, resident);
-      cfg.gridDim = dim3((unsigned)(teams * C));
       OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT>, B, P));
     }
 
@@ -125,15 +111,19 @@ namespace ofly {
       }
     }
 
+    // Sub-warp width of the pair kernels: chosen on the device, every tick, from the number of replicas selected.
+    // OFLY_GROUP pins it for tuning runs.
     struct PairGrid {
-      int G;
-      unsigned blocks;
+      int forced;       // 0: dynamic
+      unsigned blocks;  // grid-stride launch: enough blocks for the widest groups
+      long slots;       // resident threads of the chip
     };
     PairGrid pair_grid(ofly_batch *b) {
-      const size_t atoms = (size_t)b->R * b->N;
-      const int G = pick_group(b->ctx, (long)atoms);
+      int forced = env_int("OFLY_GROUP", 0);
+      if (!(forced == 4 || forced == 8 || forced == 16 || forced == 32)) forced = 0;
+      const int G = forced ? forced : 32;
       const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
-      return {G, stride_grid(b->ctx, tiles, 8)};
+      return {forced, stride_grid(b->ctx, tiles, 8), (long)b->ctx->sm_count * 2048};
     }
 
     void enqueue_rebuild(ofly_batch *b, SearchParams const &P) {
@@ -147,7 +137,7 @@ namespace ofly {
       k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb);
       k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
       const PairGrid pg = pair_grid(b);
-      switch (pg.G) {
+      switch (pg.forced) {
         case 32:
           k_nb_build<32><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
@@ -157,8 +147,11 @@ namespace ofly {
         case 8:
           k_nb_build<8><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
-        default:
+        case 4:
           k_nb_build<4><<<pg.blocks, 256, 0, st>>>(B, reb);
+          break;
+        default:
+          k_nb_build_dyn<<<pg.blocks, 256, 0, st>>>(B, reb, pg.slots);
           break;
       }
       OFLY_CUDA(cudaGetLastError());
@@ -172,7 +165,7 @@ namespace ofly {
       const unsigned long long *goff = &P.state->gdst;
       const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
       const PairGrid pg = pair_grid(b);
-      switch (pg.G) {
+      switch (pg.forced) {
         case 32:
           k_eam_rho<32><<<pg.blocks, 256, 0, st>>>(B, T, act);
           k_eam_force<32><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
@@ -185,9 +178,13 @@ namespace ofly {
           k_eam_rho<8><<<pg.blocks, 256, 0, st>>>(B, T, act);
           k_eam_force<8><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
           break;
-        default:
+        case 4:
           k_eam_rho<4><<<pg.blocks, 256, 0, st>>>(B, T, act);
           k_eam_force<4><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
+          break;
+        default:
+          k_eam_rho_dyn<<<pg.blocks, 256, 0, st>>>(B, T, act, pg.slots);
+          k_eam_force_dyn<<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride, pg.slots);
           break;
       }
       OFLY_CUDA(cudaGetLastError());
