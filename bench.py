@@ -40,9 +40,9 @@ CELLS, LATTICE, REPLICAS = 20, 2.8553, 64
 METRIC, UNIT = "eam_atom_gradient_evals_per_s", "atom-evals/s"
 WORKLOAD = "C2: bcc Fe 20^3 (a=2.8553) - 1 vacancy + 1 H = 16000 atoms, Wen Fe-H EAM, 64 concurrent dimer searches (Dimer::find_sp, default options)"
 CPU_SAMPLE_MAX_STEPS = 40  # translation steps per CPU search in the bounded sample
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_rho + k_eam_force launch pair on this workload, from the ncu --set full
-# capture summarised in profiles/ (None until a capture of the current kernels is committed)
-NCU_TRAFFIC = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_rho<4> + k_eam_force<4> launch pair on this workload, from the
+# ncu --set full capture profiles/r1n_eam_pair.txt: (403.1 + 31.1) + (404.0 + 23.5) MB
+NCU_TRAFFIC = 861.7e6
 
 
 def peaks():

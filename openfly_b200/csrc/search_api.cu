@@ -58,11 +58,13 @@ namespace ofly {
       while (t.threads < kSegMaxThreads && n3 > (long)t.threads * 2) t.threads *= 2;
       if (t.threads == kSegMaxThreads) {
         while (t.cluster < 8 && n3 > (long)t.cluster * t.threads * 8) t.cluster *= 2;
+        // 16 CTAs (one GPC's worth; non-portable cluster size) once 8 would leave > 8 elements per thread
+        if (t.cluster == 8 && n3 > 8L * t.threads * 8 && env_int("OFLY_CLUSTER16", 1)) t.cluster = 16;
       }
       int ft = env_int("OFLY_TEAM_THREADS", 0);  // tuning overrides
       if (ft == 128 || ft == 256 || ft == 512) t.threads = ft, t.cluster = 1;
       int forced = env_int("OFLY_CLUSTER", 0);
-      if (forced == 1 || forced == 2 || forced == 4 || forced == 8) t.cluster = forced;
+      if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) t.cluster = forced;
       return t;
     }
 
@@ -79,6 +81,13 @@ namespace ofly {
       attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = C > 1 ? 1 : 0;
+      if (C > 8) {
+        static bool allowed = false;  // per instantiation
+        if (!allowed) {
+          OFLY_CUDA(cudaFuncSetAttribute(k_segment<C, MAXT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+          allowed = true;
+        }
+      }
       OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT>, B, P));
     }
 
@@ -92,6 +101,9 @@ namespace ofly {
       ofly_ctx *ctx = b->ctx;
       BatchDev const &B = b->d;
       switch (shape.cluster) {
+        case 16:
+          launch_segment<16, kSegMaxThreads>(ctx, b, shape.threads, B, P);
+          break;
         case 8:
           launch_segment<8, kSegMaxThreads>(ctx, b, shape.threads, B, P);
           break;

@@ -1,0 +1,139 @@
+"""GPU parity at BASELINE.json's full sizes. Where the CPU oracle finishes in seconds it is the checker (C4: one
+250k-atom gradient; C2: sampled replicas of the 64 x 16 000 batch); beyond that, size-independent properties:
+net force zero (translation invariance of the EAM), update(+d) then update(-d) is the identity, a rebuild at the
+updated positions reproduces the updated list's gradient, replicas of a batch do not influence each other."""
+import numpy as np
+import pytest
+
+from tests.common import WEN, pair_multiset
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from openfly_b200 import fly
+
+    ctx = fly.Context(0)
+    data = fly.DataEAM(ctx, WEN)
+    yield fly, ctx, data
+    data.close()
+    ctx.close()
+
+
+def test_c4_quarter_million_atoms(gpu, oracle_lib):
+    """C4: bcc Fe 50^3, 1 % vacancies, jitter N(0, 0.05): cells + counts bit-exact, E 1e-10, forces 1e-9 vs the oracle."""
+    from openfly_b200 import inputs
+
+    fly, ctx, data = gpu
+    pos, ex, ids = inputs.vacancy_cell(50, 2.8553, 0.01, 0.05, seed=4331)
+    assert len(ids) == 247500
+    r_list = 5.3 + 0.002 + (1.1 ** (1 / 3) - 1) * 5.302  # the dimer's list radius
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, r_list)
+    nl.rebuild(pos)
+    tab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(tab, ex)
+    osys.rebuild(r_list, pos, 8)
+    c0, i0, s0 = osys.export()
+    c1, i1, s1 = nl.export()
+    assert np.array_equal(c0, c1) and np.array_equal(osys.cells(), nl.cells())
+    sample = np.random.default_rng(0).choice(len(ids), 2000, replace=False)  # full multiset compare on a sample (python loops)
+    o0, o1 = np.concatenate([[0], np.cumsum(c0)]), np.concatenate([[0], np.cumsum(c1)])
+    for a in sample:
+        assert sorted(zip(i0[o0[a]:o0[a + 1]].tolist(), s0[o0[a]:o0[a + 1]].tolist())) == \
+            sorted(zip(i1[o1[a]:o1[a + 1]].tolist(), s1[o1[a]:o1[a + 1]].tolist()))
+    pot = fly.Generic(data)
+    fz = np.zeros(len(ids), np.uint8)
+    E, Eo = pot.energy(nl)[0], osys.energy(ids, 8)
+    assert abs(E - Eo) <= 1e-10 * abs(Eo)
+    g, go = pot.gradient(nl)[0], osys.gradient(ids, fz, 8)
+    assert np.abs(g - go).max() < 1e-9
+    assert np.abs(g.sum(axis=0)).max() < 1e-8  # net force
+    s.close()
+
+
+def test_c2_batch_properties_and_sampled_oracle(gpu, oracle_lib):
+    """C2: 64 replicas x 16 000 atoms (Fe + vacancy + H)."""
+    from openfly_b200 import inputs
+
+    fly, ctx, data = gpu
+    base, ex, ids = inputs.iron_hydrogen_cell(20, 2.8553, remove=(1,), hydrogen=True)
+    R, N = 64, len(ids)
+    assert N == 16000
+    rng = np.random.default_rng(5)
+    P = np.stack([inputs.perturb(base, ex, N - 1, np.random.default_rng([77, r]))[0] for r in range(R)])
+    r_list = 5.3 + 0.002 + (1.1 ** (1 / 3) - 1) * 5.302
+    s = fly.System(data, fly.Box(tuple(ex)), ids, replicas=R)
+    nl = fly.List(s, r_list)
+    pot = fly.Generic(data)
+    nl.rebuild(P)
+    g0 = pot.gradient(nl)
+    E0 = pot.energy(nl)
+    assert np.abs(g0.sum(axis=1)).max() < 1e-9  # net force of every replica
+    # oracle on three replicas
+    tab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(tab, ex)
+    fz = np.zeros(N, np.uint8)
+    for r in (0, 31, 63):
+        osys.rebuild(r_list, P[r], 8)
+        c0, i0, s0 = osys.export()
+        c1, i1, s1 = nl.export(r)
+        assert np.array_equal(c0, c1) and np.array_equal(osys.cells(), nl.cells(r))
+        assert pair_multiset(c0[:500], i0, s0) == pair_multiset(c1[:500], i1, s1)
+        Eo = osys.energy(ids, 8)
+        assert abs(E0[r] - Eo) <= 1e-10 * abs(Eo)
+        assert np.abs(g0[r] - osys.gradient(ids, fz, 8)).max() < 1e-9
+    # update round trip: r - d + d; lists unchanged, gradients back to rounding
+    d = rng.normal(0, 0.01, P.shape)
+    nl.update(d)
+    g1 = pot.gradient(nl)
+    nl.update(-d)
+    g2 = pot.gradient(nl)
+    assert np.abs(g2 - g0).max() < 1e-11 and np.abs(g1 - g0).max() > 1e-4
+    # the updated list (radius > cut-off + 2 max|d|) sees the same pairs as a fresh rebuild at the moved positions
+    nl.update(d)
+    g_upd = pot.gradient(nl)
+    nl.rebuild(P - d)
+    assert np.abs(pot.gradient(nl) - g_upd).max() < 1e-10
+    s.close()
+    # independence: replica 5 alone gives the bits it gave inside the batch (same sub-warp width forced)
+    s1 = fly.System(data, fly.Box(tuple(ex)), ids, replicas=1)
+    nl1 = fly.List(s1, r_list)
+    nl1.rebuild(P[5])
+    assert np.abs(pot.gradient(nl1)[0] - g0[5]).max() < 1e-12
+    s1.close()
+
+
+def test_c5_sized_search_batch_properties(gpu):
+    """C5-sized shard (256 of the 2048 C3-sized searches a GPU owns at 8 GPUs): every exit is one of the reference's codes,
+    successes sit on a saddle (|g| small, positive barrier), and a second run of the same batch is bit-identical."""
+    from openfly_b200 import inputs
+
+    fly, ctx, data = gpu
+    base, ex, ids = inputs.iron_hydrogen_cell(6, 2.855, remove=(1,), hydrogen=True)
+    pot = fly.Generic(data)
+    s1 = fly.System(data, fly.Box(tuple(ex)), ids)
+    rmin, _, failed, _ = fly.LBFGS().minimise(s1, base, pot)
+    assert not failed[0]
+    nl1 = fly.List(s1, data.rcut())
+    nl1.rebuild(rmin[0])
+    e_min = pot.energy(nl1)[0]
+    s1.close()
+    R = 256
+    P, A = inputs.perturbed_batch(rmin[0], ex, len(ids) - 1, R, seed=5)
+    sR = fly.System(data, fly.Box(tuple(ex)), ids, replicas=R)
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(sR, P, A, rmin[0], pot)
+    assert set(code.tolist()) <= {0, -1, -2, -3, -5}
+    assert (code == 0).sum() > R // 4
+    ok = code == 0
+    final = np.where(ok[:, None, None], out_r, rmin[0][None])  # a replica that ran off the tables (-5) ends on overlapping atoms
+    nl = fly.List(sR, data.rcut())
+    nl.rebuild(final)
+    E, g = pot.energy(nl), pot.gradient(nl)
+    assert (E[ok] - e_min).min() > 0
+    # converged: the dimer stops on the EFFECTIVE gradient (|g_eff| < 1e-5); the true gradient is then small too
+    assert np.sqrt((g[ok] ** 2).sum(axis=(1, 2))).max() < 1e-3
+    again = fly.Dimer().find_sp(sR, P, A, rmin[0], pot)
+    assert np.array_equal(again[2], code) and np.array_equal(again[0], out_r) and np.array_equal(again[3], cnt)
+    sR.close()
