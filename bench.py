@@ -271,6 +271,17 @@ def run_b200(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU legs use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which
+    would otherwise turn the all-core baseline into a single-core one)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def oracle_fast_lib():
     """The oracle built with the reference's flags (-O3 -march=native) for THIS host when g++ is present,
     else the prebuilt x86-64-v3 file that travelled with the repository."""
@@ -288,10 +299,11 @@ def oracle_fast_lib():
 
 
 def cpu_baseline(rmin, ex, ids, P, A, steps: int):
+    n_threads = host_threads()
     O, path, flags = oracle_fast_lib()
     tab = O.Tables(WEN, fast=True, libpath=path)
     osys = O.System(tab, ex)
-    cores = tab.L.max_threads()
+    cores = max(tab.L.max_threads(), n_threads)
     fz = np.zeros(len(ids), np.uint8)
     iopt = O.DIMER_IOPT.copy()
     iopt[1] = CPU_SAMPLE_MAX_STEPS
@@ -314,12 +326,13 @@ def run_reference(args):
         return
     from openfly_b200 import inputs
 
+    n_threads = host_threads()
     O, path, flags = oracle_fast_lib()
     tab = O.Tables(WEN, fast=True, libpath=path)
     pos, ex, ids, _ = build_inputs(args.seed)
     N = len(ids)
     osys = O.System(tab, ex)
-    cores = tab.L.max_threads()
+    cores = max(tab.L.max_threads(), n_threads)
     fz = np.zeros(N, np.uint8)
     rmin, _, failed, _ = osys.minimise(pos, ids, fz, threads=cores)
     assert not failed

@@ -179,6 +179,7 @@ namespace ofly {
     double *red;    // shared: [2][C][kMaxRed] cluster slots, then [2][32][kMaxRed] warp partials
     uint64_t *bar;  // shared: [3] mbarriers: one per slot buffer, one for reduce_wide (clusters only)
     GramShared<C> *gram = nullptr;
+    double *scal = nullptr;  // shared: 8 doubles, scalars computed by warp 0 for the whole CTA (share_scalars)
     const SearchParams *trace_params = nullptr;  // set per replica by the segment (tuning aid)
     int trace_r = -1;
     __device__ __forceinline__ void mark(int id) const {
@@ -256,6 +257,25 @@ namespace ofly {
         }
       }
       parity ^= 1;
+    }
+
+    // Transcendental scalar algebra is done by ONE warp per CTA and broadcast through shared memory: sixteen warps
+    // evaluating the same fp64 sin/cos/atan chains would queue on the SM's FP64 pipe for several microseconds.
+    // f(out) fills out[0..n); every CTA of a team computes the same bits from the same inputs.
+    template <int N, typename F>
+    __device__ __forceinline__ void share_scalars(double (&out)[N], F &&f) {
+      static_assert(N <= 8, "scal holds 8 doubles");
+      if (threadIdx.x < 32) {
+        f(out);
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int q = 0; q < N; q++) scal[q] = out[q];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < N; q++) out[q] = scal[q];
+      __syncthreads();  // scal may be rewritten right away
     }
 
     // Sum nv <= kGramMax values over the team. In: gram->part[warp][v] written by lane 0 of every warp;
@@ -894,14 +914,21 @@ namespace ofly {
           team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int, const double(&v)[3]) { a1[0] = fma(v[0] - v[1], v[2], a1[0]); });
         }
         tm.reduce<1>(a1);
-        const double s1 = sin(theta_1);
-        const double c_x1 = a1[0] / dr;
-        const double a_1 = (c_x0 - c_x1 + b_1 * sin(2 * theta_1)) / (1 - cos(2 * theta_1));
-        double theta_min = 0.5 * atan(b_1 / a_1);
-        if (a_1 * cos(2 * theta_min) - a_1 + b_1 * sin(2 * theta_min) > 0) theta_min += M_PI / 2;  // extremum was a maximum
-
-        const double cm = cos(theta_min), sm = sin(theta_min);
-        const double k1 = sin(theta_1 - theta_min) / s1, k2 = sm / s1, k3 = 1 - cm - sm * tan(0.5 * theta_1);
+        double sc[6];  // theta_min, cos, sin, k1, k2, k3
+        {
+          const double th1 = theta_1, cx0 = c_x0, b1 = b_1, a1v = a1[0];
+          tm.share_scalars(sc, [&](double(&o)[6]) {
+            const double s1 = sin(th1);
+            const double c_x1 = a1v / dr;
+            const double a_1 = (cx0 - c_x1 + b1 * sin(2 * th1)) / (1 - cos(2 * th1));
+            double tmin = 0.5 * atan(b1 / a_1);
+            if (a_1 * cos(2 * tmin) - a_1 + b1 * sin(2 * tmin) > 0) tmin += M_PI / 2;  // extremum was a maximum
+            const double cmv = cos(tmin), smv = sin(tmin);
+            o[0] = tmin, o[1] = cmv, o[2] = smv;
+            o[3] = sin(th1 - tmin) / s1, o[4] = smv / s1, o[5] = 1 - cmv - smv * tan(0.5 * th1);
+          });
+        }
+        const double theta_min = sc[0], cm = sc[1], sm = sc[2], k1 = sc[3], k2 = sc[4], k3 = sc[5];
         // The same pass accumulates what the next rotation iteration's torque needs ((g1-g0).axis and the component
         // sums of g1-g0 and axis), element by element exactly as the separate pass below would.
         {
@@ -974,13 +1001,21 @@ namespace ofly {
         const double inv_th = 1 / sqrt(a2[0]);
         b_1 = a2[1] * inv_th / dr;
         c_x0 = pax / dr;
-        theta_1 = -0.5 * atan(b_1 / fabs(c_x0));
+        double st[3];  // theta_1, cos, sin
+        {
+          const double b1 = b_1, cx0 = c_x0;
+          tm.share_scalars(st, [&](double(&o)[3]) {
+            o[0] = -0.5 * atan(b1 / fabs(cx0));
+            o[1] = cos(o[0]), o[2] = sin(o[0]);
+          });
+        }
+        theta_1 = st[0];
 
         if (fabs(theta_1) < P.rot_theta_tol || (rot_it >= P.iter_max_rot && c_x0 < 0) || rot_it > 10 * P.iter_max_rot) {
           curv = c_x0;
         } else {
           // trial axis, move the list end-point from the old offset to the new one (rotor.cpp:111-116)
-          const double c1 = cos(theta_1), s1 = sin(theta_1);
+          const double c1 = st[1], s1 = st[2];
           {
             const double *const src[3] = {theta, W.axis, W.dprev};
             team_pass<3>(tm.tid, tm.nthreads, n3, src, [&](int t, const double(&v)[3]) {
@@ -1081,10 +1116,12 @@ namespace ofly {
     __shared__ double red_smem[team_smem_doubles(C)];
     __shared__ uint64_t red_bar[3];
     __shared__ GramShared<C> gram_smem;
+    __shared__ double scal_smem[8];
     __shared__ int last_team;
 
     Team<C> tm(red_smem, red_bar);
     tm.gram = &gram_smem;
+    tm.scal = scal_smem;
     // Team t owns entry t of the list of replicas that were active after the previous tick (tick 0: all); the
     // teams beyond the list leave at once. (A loop over entries inside the kernel would let the compiler hoist
     // every loop-invariant address out of it and spill them all.)
