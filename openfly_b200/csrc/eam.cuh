@@ -197,22 +197,37 @@ namespace ofly {
   // a batch only a few replicas are left and the evaluation is a latency chain, not a throughput problem.
   // (The lane count sets the order of the per-atom sum, so a replica's rounding depends on how many replicas are
   // active with it: deterministic for a given batch, not identical across batch compositions.)
-  static __global__ void __launch_bounds__(256) k_eam_rho_dyn(BatchDev B, TablesDev T, Sel S, long slots) {
+  // trace (tuning aid, may be null): [0] = count, then (mark, globaltimer) pairs -- block 0 stamps its start and end
+  __device__ __forceinline__ void kernel_stamp(unsigned long long *trace, int cap, int mark) {
+    if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      unsigned long long slot = atomicAdd(trace, 1ull);
+      if (slot < (unsigned long long)cap) trace[1 + 2 * slot] = (unsigned long long)mark, trace[2 + 2 * slot] = t;
+    }
+  }
+
+  static __global__ void __launch_bounds__(256) k_eam_rho_dyn(BatchDev B, TablesDev T, Sel S, long slots, unsigned long long *trace, int trace_cap) {
+    kernel_stamp(trace, trace_cap, 91);
     switch (group_for((long)(*S.count) * B.N, slots)) {
       case 4: eam_rho_tiles<4>(B, T, S); break;
       case 8: eam_rho_tiles<8>(B, T, S); break;
       case 16: eam_rho_tiles<16>(B, T, S); break;
       default: eam_rho_tiles<32>(B, T, S); break;
     }
+    kernel_stamp(trace, trace_cap, 92);
   }
   static __global__ void __launch_bounds__(256) k_eam_force_dyn(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
-                                                                const unsigned long long *__restrict__ offset, size_t offset_stride, long slots) {
+                                                                const unsigned long long *__restrict__ offset, size_t offset_stride, long slots,
+                                                                unsigned long long *trace, int trace_cap) {
+    kernel_stamp(trace, trace_cap, 93);
     switch (group_for((long)(*S.count) * B.N, slots)) {
       case 4: eam_force_tiles<4>(B, T, S, out, stride, offset, offset_stride); break;
       case 8: eam_force_tiles<8>(B, T, S, out, stride, offset, offset_stride); break;
       case 16: eam_force_tiles<16>(B, T, S, out, stride, offset, offset_stride); break;
       default: eam_force_tiles<32>(B, T, S, out, stride, offset, offset_stride); break;
     }
+    kernel_stamp(trace, trace_cap, 94);
   }
 
   // Per-atom energy e_i = 0.5 sum V + F(rho) into scratch[R][N] (all replicas).

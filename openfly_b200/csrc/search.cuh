@@ -1201,6 +1201,7 @@ namespace ofly {
           __threadfence();
           if (P.use_cond) cudaGraphSetConditional(P.cond, (na > 0 && tick <= P.max_ticks) ? 1u : 0u);
           if (P.use_cond_rebuild) cudaGraphSetConditional(P.cond_rebuild, nr > 0 ? 1u : 0u);
+          if (P.trace != nullptr) trace_mark(P, P.trace_replica, 0, 95);  // end of the tick's bookkeeping
         }
       }
     }

@@ -195,8 +195,8 @@ namespace ofly {
           k_eam_force<4><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
           break;
         default:
-          k_eam_rho_dyn<<<pg.blocks, 256, 0, st>>>(B, T, act, pg.slots);
-          k_eam_force_dyn<<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride, pg.slots);
+          k_eam_rho_dyn<<<pg.blocks, 256, 0, st>>>(B, T, act, pg.slots, P.trace, P.trace_cap);
+          k_eam_force_dyn<<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride, pg.slots, P.trace, P.trace_cap);
           break;
       }
       OFLY_CUDA(cudaGetLastError());
