@@ -410,6 +410,7 @@ void ofly_batch_destroy(ofly_batch *b) {
   b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->cell_items.release();
   b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release(), b->sel_all.release();
   b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();
+  for (auto &buf : b->io_pool) buf.release();
   ofly_tables_release(b->tables);
   delete b;
 }

@@ -186,11 +186,14 @@ namespace ofly {
   // Sub-warp width for `atoms` atoms of work on a chip with `slots` resident threads: few atoms -> wide groups
   // (more threads, shorter per-lane chains: latency), many atoms -> narrow groups (fewer idle lanes on the ragged
   // row tail: throughput).
+  // Measured on a lone 16 000-atom replica: the widest group that still fits ONE wave of resident threads (the pair
+  // kernels hold ~1024 threads per SM, half of `slots`) is the fastest; a second wave costs more than longer lanes.
   __host__ __device__ inline int group_for(long atoms, long slots) {
-    if (atoms * 4 >= 2 * slots) return 4;
-    if (atoms * 8 >= 2 * slots) return 8;
-    if (atoms * 16 >= slots) return 16;
-    return 32;
+    const long wave = slots / 2;
+    if (atoms * 32 <= wave) return 32;
+    if (atoms * 16 <= wave) return 16;
+    if (atoms * 8 <= wave) return 8;
+    return 4;
   }
 
   // The search's tick kernels pick G on the device from the number of replicas still active: for most ticks of

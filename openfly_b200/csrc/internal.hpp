@@ -83,6 +83,7 @@ struct ofly_batch {
   ofly::DevBuf<int> cnt, cell_of, cell_count, cell_start, fault;
   ofly::DevBuf<int> sel_all;  // [R + 1]: 0..R-1 then R -- the "every replica" selection of the grid kernels
   ofly::DevBuf<double> stage_a, stage_b, stage_c, scratch;  // [R][3N] staging for the host-pointer entry points
-  ofly::DevBuf<char> search_ws;                              // workspace of the persistent search kernels
+  ofly::DevBuf<char> search_ws;                              // workspace of the search engine
+  std::vector<ofly::DevBuf<char>> io_pool;                   // device staging of the host-pointer search calls
   std::vector<int> fault_host;
 };

@@ -272,15 +272,15 @@ namespace ofly {
   // Sub-warp width picked on the device from the number of selected replicas (the stored row is a compaction in
   // candidate order, so the list does not depend on G).
   static __global__ void __launch_bounds__(256) k_nb_build_dyn(BatchDev B, Sel S, long slots) {
-    const long atoms = (long)(*S.count) * B.N;
-    if (atoms * 4 >= 2 * slots) {
-      nb_build_tiles<4>(B, S);
-    } else if (atoms * 8 >= 2 * slots) {
-      nb_build_tiles<8>(B, S);
-    } else if (atoms * 16 >= slots) {
-      nb_build_tiles<16>(B, S);
-    } else {
+    const long atoms = (long)(*S.count) * B.N, wave = slots / 2;  // same rule as group_for (eam.cuh)
+    if (atoms * 32 <= wave) {
       nb_build_tiles<32>(B, S);
+    } else if (atoms * 16 <= wave) {
+      nb_build_tiles<16>(B, S);
+    } else if (atoms * 8 <= wave) {
+      nb_build_tiles<8>(B, S);
+    } else {
+      nb_build_tiles<4>(B, S);
     }
   }
 

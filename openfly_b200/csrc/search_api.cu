@@ -458,25 +458,23 @@ namespace ofly {
       return P;
     }
 
-    // Host-pointer staging: one device arena per call.
+    // Host-pointer staging: the k-th buffer a call asks for is the k-th buffer of the batch's pool (grown on demand,
+    // kept until the batch goes), so a search call through host pointers does no cudaMalloc / cudaFree of its own.
     struct Arena {
-      ofly_ctx *ctx;
-      std::vector<void *> ptrs;
-      explicit Arena(ofly_ctx *c) : ctx(c) {}
-      ~Arena() {
-        for (void *p : ptrs) cudaFree(p);
-      }
+      ofly_batch *b;
+      size_t next = 0;
+      explicit Arena(ofly_batch *batch) : b(batch) {}
       template <typename T>
       T *alloc(size_t n) {
-        void *p = nullptr;
-        OFLY_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-        ptrs.push_back(p);
-        return static_cast<T *>(p);
+        if (next == b->io_pool.size()) b->io_pool.emplace_back();
+        DevBuf<char> &buf = b->io_pool[next++];
+        buf.reserve(std::max<size_t>(n, 1) * sizeof(T));
+        return reinterpret_cast<T *>(buf.p);
       }
       template <typename T>
       T *upload(const T *host, size_t n) {
         T *d = alloc<T>(n);
-        if (n) OFLY_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        if (n) OFLY_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, b->ctx->stream));
         return d;
       }
     };
@@ -518,7 +516,7 @@ int ofly_lbfgs_minimise(ofly_batch *b, const ofly_lbfgs_options *opt, const doub
     require(b && opt && pos_in_host && pos_out_host && status_host, "null argument");
     OFLY_CUDA(cudaSetDevice(b->ctx->device));
     size_t nv = (size_t)b->R * 3 * (size_t)b->N, R = (size_t)b->R;
-    Arena A(b->ctx);
+    Arena A(b);
     DevPtrs io{};
     io.pos_in = A.upload(pos_in_host, nv);
     io.pos_out = A.alloc<double>(nv);
@@ -557,7 +555,7 @@ int ofly_dimer_find_sp(ofly_batch *b, const ofly_dimer_options *opt, const ofly_
     require(n_hist == 0 || (in_min_host && hist_sp_host), "history given without in_min / hist_sp");
     OFLY_CUDA(cudaSetDevice(b->ctx->device));
     size_t n3 = 3 * (size_t)b->N, nv = (size_t)b->R * n3, R = (size_t)b->R;
-    Arena A(b->ctx);
+    Arena A(b);
     DevPtrs io{};
     io.pos_in = A.upload(pos_in_host, nv);
     io.axis_in = A.upload(axis_in_host, nv);
