@@ -309,3 +309,44 @@ class Dimer:
         if raise_oob and (code == -5).any():
             raise OutOfBounds(capi.OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region")
         return out_r, out_ax, code, cnt
+
+
+# ---- Vineyard prefactor from mass-weighted Hessians (host side: the dense eigensolve is SURVEY.md 8(f2), not on the GPU) ----
+
+def hessian_eigenvalues(hess_lower: np.ndarray) -> np.ndarray:
+    """system::Hessian::eigenvalues (hessian.hpp:86-93): ascending eigenvalues of the symmetric matrix whose LOWER
+    triangle is given (Eigen's SelfAdjointEigenSolver reads the lower triangle only)."""
+    h = np.tril(hess_lower)
+    return np.linalg.eigvalsh(h + np.tril(h, -1).T)
+
+
+def log_prod_eigen_minimum(eigs: np.ndarray, count_frozen: int = 0, zero_tol: float = 1e-6):
+    """Master::calc_minima_hess (find.cpp:1105-1135): sum of log(lambda) over the non-zero modes of the minimum; every mode
+    must be > -zero_tol and the number of zero modes must be 3 (3 * count_frozen when atoms are frozen)."""
+    if (eigs < -zero_tol).any():
+        raise OflyError(capi.OFLY_ERR_INVALID, f"Mode has eigenvalue = {eigs.min()}")
+    nz = eigs > zero_tol
+    zeros = int((~nz).sum())
+    expect = 3 * count_frozen if count_frozen > 0 else 3
+    if zeros != expect:
+        raise OflyError(capi.OFLY_ERR_INVALID, f"Expecting {expect} zero modes but fount {zeros}")
+    return float(np.log(eigs[nz]).sum()), zeros
+
+
+def vineyard_prefactor(eigs_min: np.ndarray, eigs_sp: np.ndarray, count_frozen: int = 0, zero_tol: float = 1e-6):
+    """Harmonic-TST prefactor as saddle::Master computes it (find.cpp:284-290, 846-871): the saddle needs exactly one
+    negative mode (index 0), the same number of zero modes as the minimum, and
+        nu = sqrt(exp(sum log lambda_min - sum log lambda_sp) / (2 pi 1.6605390666050e-27)).
+    Returns None for a second-or-higher-order saddle (the reference discards the mechanism)."""
+    log_min, zeros_min = log_prod_eigen_minimum(eigs_min, count_frozen, zero_tol)
+    if not eigs_sp[0] < -zero_tol:
+        raise OflyError(capi.OFLY_ERR_INVALID, f"Saddle-point with minimum mode={eigs_sp[0]}")
+    rest = eigs_sp[1:]
+    if (rest < -zero_tol).any():
+        return None
+    nz = rest > zero_tol
+    zeros = int((~nz).sum())
+    if zeros != zeros_min:
+        raise OflyError(capi.OFLY_ERR_INVALID, f"Expecting {zeros_min} zero modes but hessian has {zeros}")
+    log_sp = float(np.log(rest[nz]).sum())
+    return float(np.sqrt(np.exp(log_min - log_sp) / (2 * np.pi * 1.6605390666050e-27)))

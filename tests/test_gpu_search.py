@@ -238,3 +238,87 @@ def test_out_of_bounds_reported_per_replica(gpu, small_cell):
     with pytest.raises(fly.OutOfBounds):
         fly.Dimer().find_sp(s, bad, A[:3], r0, fly.Generic(data), raise_oob=True)
     s.close()
+
+
+def test_barriers_and_vineyard_prefactors_c3(gpu, otab, oracle_lib):
+    """C3's deliverable: for every saddle found, barrier (1e-6 eV) and harmonic prefactor (1e-4 relative, BASELINE north
+    star) from the GPU's mass-weighted Hessians against the same quantities from the oracle's Hessians.
+    find.cpp:284-290,846-871,1105-1135."""
+    fly, ctx, data = gpu
+    base, ex, ids = bcc_vacancy(5, a=2.855, remove=(1,), hydrogen=True)  # 250 atoms: the dense eigensolves stay cheap
+    fz = np.zeros(len(ids), np.uint8)
+    osys = oracle_lib.System(otab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=8)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(16)]
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    pot = fly.Generic(data)
+    sR = fly.System(data, fly.Box(tuple(ex)), ids, replicas=len(P))
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(sR, P, A, r0, pot)
+    sR.close()
+    o_r, o_ax, o_code, o_cnt = osys.find_sp_batch(P, A, ids, fz, r0, threads=8)
+    # searches that reached the same saddle on both sides (a long trajectory may branch out, see the 64-search test)
+    both = [k for k in range(len(P)) if code[k] == 0 and o_code[k] == 0 and np.abs(out_r[k] - o_r[k]).max() < 1e-4]
+    assert len(both) >= 3
+
+    s1 = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s1, data.rcut())
+
+    def gpu_point(r):
+        nl.rebuild(r)
+        return pot.energy(nl)[0], fly.hessian_eigenvalues(pot.hessian(nl, mass_weight=True))
+
+    def cpu_point(r):
+        osys.rebuild(otab.rcut, r, 8)
+        return osys.energy(ids, 8), fly.hessian_eigenvalues(osys.hessian(ids, fz, 8, mass_weight=True))
+
+    e_min, ev_min = gpu_point(r0)
+    eo_min, evo_min = cpu_point(r0)
+    n = 0
+    for k in both[:4]:
+        e_sp, ev_sp = gpu_point(out_r[k])
+        eo_sp, evo_sp = cpu_point(o_r[k])
+        assert abs((e_sp - e_min) - (eo_sp - eo_min)) < 1e-6
+        nu, nu_o = fly.vineyard_prefactor(ev_min, ev_sp), fly.vineyard_prefactor(evo_min, evo_sp)
+        assert (nu is None) == (nu_o is None)
+        if nu is not None:
+            assert abs(nu / nu_o - 1) < 1e-4
+            assert 1e11 < nu < 1e16  # an attempt frequency, in Hz
+            n += 1
+    assert n >= 1
+    s1.close()
+
+
+def test_dimer_64_searches_branch_outs_classified(gpu, otab, oracle_lib, capsys):
+    """64 searches on the apps/hydrogen-sized cell against the oracle. Trajectories are chaotic: a
+    rounding-level difference can send a long search to another saddle. So every search is CLASSIFIED -- same exit and
+    same saddle (then the barrier must agree to 1e-6 eV), or branched out -- and branch-outs must stay rare."""
+    fly, ctx, data = gpu
+    base, ex, ids = bcc_vacancy(6, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    osys = oracle_lib.System(otab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=8)
+    assert not failed
+    R = 64
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(R)]
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    sR = fly.System(data, fly.Box(tuple(ex)), ids, replicas=R)
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(sR, P, A, r0, fly.Generic(data))
+    sR.close()
+    o_r, o_ax, o_code, o_cnt = osys.find_sp_batch(P, A, ids, fz, r0, threads=8)
+    E0 = _energy(osys, otab, ids, r0)
+    same, branched = 0, []
+    for k in range(R):
+        if code[k] != o_code[k]:
+            branched.append((k, int(code[k]), int(o_code[k]), int(cnt[k, 0]), int(o_cnt[k, 0])))
+        elif code[k] == 0 and np.abs(out_r[k] - o_r[k]).max() > 1e-4:
+            branched.append((k, 0, 0, int(cnt[k, 0]), int(o_cnt[k, 0])))
+        else:
+            same += 1
+            if code[k] == 0:
+                assert abs((_energy(osys, otab, ids, out_r[k]) - E0) - (_energy(osys, otab, ids, o_r[k]) - E0)) < 1e-6
+    with capsys.disabled():
+        print(f"\n[dimer parity] {same}/{R} searches identical in exit and saddle; branch-outs (replica, exit gpu, exit cpu, evals gpu, evals cpu): {branched}")
+    assert len(branched) <= R // 10
+    # a branch-out only happens on long trajectories: the short ones must all agree
+    assert all(min(b[3], b[4]) > 150 for b in branched)
