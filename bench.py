@@ -216,6 +216,39 @@ def run_b200(args):
     n2 = fly.List(sysR, 0).mean_count()
     grad_leg = {"atom_evals_per_s": R * N / (gms * 1e-3), "ms_per_launch_pair": gms, "mean_neighbours": n2, "launch_pairs_timed": iters}
 
+    # neigh::List::rebuild of the same batch (six kernels per call), and the C4 single-system study (rank 0 only)
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        ctx.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            fn()
+        b.record(stream)
+        ctx.synchronize()
+        return a.elapsed_time(b) / n
+
+    rb_ms = timed(lambda: capi.check(lib.ofly_neigh_rebuild_dev(sysR.h, r_list, d_pos)), 10)
+    rebuild_leg = {"atoms_per_s": R * N / (rb_ms * 1e-3), "ms_per_rebuild": rb_ms, "algorithmic_bytes_per_atom": 24 + 4 * n2 + 16,
+                   "hbm_frac": R * N / (rb_ms * 1e-3) * (24 + 4 * n2 + 16) / 1e9 / peaks()[0]}
+    c4_leg = None
+    if rank == 0 and not args.no_c4:
+        p4, ex4, id4 = inputs.vacancy_cell(50, LATTICE, 0.01, 0.05, seed=4331)
+        s4 = fly.System(data, fly.Box(tuple(ex4)), id4)
+        d4, g4 = ctx.alloc(p4.nbytes), ctx.alloc(p4.nbytes)
+        ctx.upload(d4, p4)
+        rb4 = timed(lambda: capi.check(lib.ofly_neigh_rebuild_dev(s4.h, r_list, d4)), 10)
+        gr4 = timed(lambda: capi.check(lib.ofly_eam_gradient_dev(s4.h, g4)), 20)
+        nb4 = fly.List(s4, 0).mean_count()
+        c4_leg = {"workload": "C4: bcc Fe 50^3, 1 % vacancies, jitter N(0, 0.05 A): one 247 500-atom system, dimer list radius",
+                  "atoms": len(id4), "mean_neighbours": nb4,
+                  "gradient_atom_evals_per_s": len(id4) / (gr4 * 1e-3), "gradient_ms": gr4,
+                  "gradient_hbm_frac": len(id4) / (gr4 * 1e-3) * (8 * nb4 + 64) / 1e9 / peaks()[0],
+                  "rebuild_atoms_per_s": len(id4) / (rb4 * 1e-3), "rebuild_ms": rb4}
+        ctx.free(d4), ctx.free(g4)
+        s4.close()
+
     # reduce over ranks: max time, sum of work
     if world > 1:
         t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
@@ -260,7 +293,10 @@ def run_b200(args):
                          "note": "bound in practice by the L1 data pipe (one wavefront per gathered 32 B sector), see DESIGN.md 4 and profiles/; "
                                  "the search step as a whole moves %.1f GB/s of algorithmic gradient bytes" % (evals_step * N * b_alg / (sec / args.steps) / 1e9)},
             "clocks": clocks.summary(),
+            "neighbour_rebuild": rebuild_leg,
         }
+        if c4_leg:
+            out["c4_single_system"] = c4_leg
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(rmin, ex, ids, P, A, steps=1)
         print(json.dumps(out), flush=True)
@@ -372,6 +408,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=1334)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 single-system leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

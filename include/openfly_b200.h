@@ -118,6 +118,10 @@ int ofly_eam_gradient_dev(ofly_batch *b, double *grad_dev);
 /* hessian (eam.cpp:122-233) of one replica: dense column-major (3N)^2, lower triangle meaningful,
  * zero rows/cols for frozen atoms. mass_weight != 0 applies Hessian::mass_weight (hessian.hpp:136-143). */
 int ofly_eam_hessian(ofly_batch *b, long replica, int mass_weight, double *hess_host);
+/* Hessian::eigenvalues() (hessian.hpp:86-93) of that matrix, ascending, solved on the device: out [3N]. The consumers are
+ * the Vineyard prefactors of saddle::Master (src/saddle/find.cpp:846-871, 1107-1135). Dense symmetric solve by cuSOLVER
+ * (loaded on first use); returns OFLY_ERR_CUDA if it is not installed. */
+int ofly_eam_hessian_eigenvalues(ofly_batch *b, long replica, int mass_weight, double *eig_host);
 
 /* ---- minimise::LBFGS and saddle::Dimer, whole batch resident on the device -------------------- */
 

@@ -97,6 +97,7 @@ SIGNATURES = {
                                      C.c_double, C.c_int, _dp, _dp, _ip, _lp]),
     "ofly_dimer_find_sp_dev": (C.c_int, [_vp, C.POINTER(DimerOptions), C.POINTER(RotorOptions), _vp, _vp, _vp, _vp, C.c_long,
                                          C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
+    "ofly_eam_hessian_eigenvalues": (C.c_int, [_vp, C.c_long, C.c_int, _dp]),
     "ofly_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "ofly_dev_free": (C.c_int, [_vp, _vp]),
     "ofly_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),

@@ -4,6 +4,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
 #include <new>
 
 #include "eam.cuh"
@@ -565,32 +568,103 @@ int ofly_eam_energy(ofly_batch *b, double *energy_host) {
     throw_on_fault(collect_faults(b));
   });
 }
-int ofly_eam_hessian(ofly_batch *b, long replica, int mass_weight, double *hess_host) {
-  return guarded([&] {
-    require(b && hess_host, "null argument");
+namespace ofly {
+  // Dense Hessian of one replica assembled into H (device, column-major (3N)^2, zero-initialised here).
+  static void assemble_hessian(ofly_batch *b, long replica, int mass_weight, DevBuf<double> &H, DevBuf<double> &aux, DevBuf<double> &mass) {
     require(b->built, "hessian() before rebuild()");
     require(replica >= 0 && replica < b->R, "replica out of range");
     require(b->tables->host.r_cut <= b->r_list, "r_cut is bigger than the internal r_cut");
     use(b->ctx);
     size_t n3 = 3 * (size_t)b->N;
-    DevBuf<double> H, aux, mass;
-    try {
-      H.reserve(n3 * n3), aux.reserve(4 * (size_t)b->N), mass.reserve(kMaxTypes);
-      std::vector<double> m(kMaxTypes, 1.0);
-      for (int t = 0; t < b->tables->host.n_types; t++) m[(size_t)t] = b->tables->host.mass[(size_t)t];
-      OFLY_CUDA(cudaMemcpyAsync(mass.p, m.data(), sizeof(double) * kMaxTypes, cudaMemcpyHostToDevice, b->ctx->stream));
-      OFLY_CUDA(cudaMemsetAsync(H.p, 0, sizeof(double) * n3 * n3, b->ctx->stream));
-      clear_faults(b);
-      launch(b->ctx, k_hess_rho_mu<8>, (size_t)b->N * 8, 256, b->d, b->tables->dev, (int)replica, aux.p);
-      launch(b->ctx, k_hess_columns<32>, (size_t)b->N * 32, 256, b->d, b->tables->dev, (int)replica, (const double *)aux.p, H.p);
-      if (mass_weight) launch(b->ctx, k_hess_mass_weight, n3 * n3, 256, H.p, (int)b->N, (const uint8_t *)b->type.p, (const double *)mass.p);
-      OFLY_CUDA(cudaMemcpyAsync(hess_host, H.p, sizeof(double) * n3 * n3, cudaMemcpyDeviceToHost, b->ctx->stream));
-      throw_on_fault(collect_faults(b));
-    } catch (...) {
-      H.release(), aux.release(), mass.release();
-      throw;
-    }
-    H.release(), aux.release(), mass.release();
+    H.reserve(n3 * n3), aux.reserve(4 * (size_t)b->N), mass.reserve(kMaxTypes);
+    std::vector<double> m(kMaxTypes, 1.0);
+    for (int t = 0; t < b->tables->host.n_types; t++) m[(size_t)t] = b->tables->host.mass[(size_t)t];
+    OFLY_CUDA(cudaMemcpyAsync(mass.p, m.data(), sizeof(double) * kMaxTypes, cudaMemcpyHostToDevice, b->ctx->stream));
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));  // m is a local
+    OFLY_CUDA(cudaMemsetAsync(H.p, 0, sizeof(double) * n3 * n3, b->ctx->stream));
+    clear_faults(b);
+    launch(b->ctx, k_hess_rho_mu<8>, (size_t)b->N * 8, 256, b->d, b->tables->dev, (int)replica, aux.p);
+    launch(b->ctx, k_hess_columns<32>, (size_t)b->N * 32, 256, b->d, b->tables->dev, (int)replica, (const double *)aux.p, H.p);
+    if (mass_weight) launch(b->ctx, k_hess_mass_weight, n3 * n3, 256, H.p, (int)b->N, (const uint8_t *)b->type.p, (const double *)mass.p);
+  }
+
+  struct HessBufs {
+    DevBuf<double> H, aux, mass, work, eig;
+    DevBuf<int> info;
+    ~HessBufs() { H.release(), aux.release(), mass.release(), work.release(), eig.release(), info.release(); }
+  };
+
+  // cuSOLVER is loaded on first use (dlopen), so the library itself carries no load-time dependency on it.
+  struct Cusolver {
+    void *lib = nullptr;
+    int (*create)(void **) = nullptr;
+    int (*destroy)(void *) = nullptr;
+    int (*set_stream)(void *, cudaStream_t) = nullptr;
+    int (*syevd_size)(void *, int, int, int, const double *, int, const double *, int *) = nullptr;
+    int (*syevd)(void *, int, int, int, double *, int, double *, double *, int, int *) = nullptr;
+    bool ok() const { return lib && create && destroy && set_stream && syevd_size && syevd; }
+  };
+  static Cusolver &cusolver() {
+    static Cusolver c = [] {
+      Cusolver x;
+      for (char const *name : {"libcusolver.so.11", "libcusolver.so", "libcusolver.so.12"}) {
+        x.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (x.lib) break;
+      }
+      if (x.lib) {
+        x.create = reinterpret_cast<decltype(x.create)>(dlsym(x.lib, "cusolverDnCreate"));
+        x.destroy = reinterpret_cast<decltype(x.destroy)>(dlsym(x.lib, "cusolverDnDestroy"));
+        x.set_stream = reinterpret_cast<decltype(x.set_stream)>(dlsym(x.lib, "cusolverDnSetStream"));
+        x.syevd_size = reinterpret_cast<decltype(x.syevd_size)>(dlsym(x.lib, "cusolverDnDsyevd_bufferSize"));
+        x.syevd = reinterpret_cast<decltype(x.syevd)>(dlsym(x.lib, "cusolverDnDsyevd"));
+      }
+      return x;
+    }();
+    return c;
+  }
+}  // namespace ofly
+
+int ofly_eam_hessian(ofly_batch *b, long replica, int mass_weight, double *hess_host) {
+  return guarded([&] {
+    require(b && hess_host, "null argument");
+    HessBufs B;
+    assemble_hessian(b, replica, mass_weight, B.H, B.aux, B.mass);
+    size_t n3 = 3 * (size_t)b->N;
+    OFLY_CUDA(cudaMemcpyAsync(hess_host, B.H.p, sizeof(double) * n3 * n3, cudaMemcpyDeviceToHost, b->ctx->stream));
+    throw_on_fault(collect_faults(b));
+  });
+}
+
+int ofly_eam_hessian_eigenvalues(ofly_batch *b, long replica, int mass_weight, double *eig_host) {
+  return guarded([&] {
+    require(b && eig_host, "null argument");
+    Cusolver &cs = cusolver();
+    if (!cs.ok()) throw Error(OFLY_ERR_CUDA, "libcusolver could not be loaded (needed for the dense symmetric eigenvalue solve)");
+    HessBufs B;
+    assemble_hessian(b, replica, mass_weight, B.H, B.aux, B.mass);
+    throw_on_fault(collect_faults(b));
+    const int n3 = 3 * (int)b->N;
+    void *h = nullptr;
+    if (cs.create(&h) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnCreate failed");
+    struct Guard {
+      Cusolver &c;
+      void *h;
+      ~Guard() { c.destroy(h); }
+    } guard{cs, h};
+    if (cs.set_stream(h, b->ctx->stream) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnSetStream failed");
+    B.eig.reserve((size_t)n3), B.info.reserve(1);
+    int lwork = 0;
+    // jobz = CUSOLVER_EIG_MODE_NOVECTOR (0), uplo = CUBLAS_FILL_MODE_LOWER (0): the lower triangle is what system::Hessian
+    // fills and what Eigen's SelfAdjointEigenSolver reads (hessian.hpp:86-93)
+    if (cs.syevd_size(h, 0, 0, n3, B.H.p, n3, B.eig.p, &lwork) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
+    B.work.reserve((size_t)std::max(lwork, 1));
+    if (cs.syevd(h, 0, 0, n3, B.H.p, n3, B.eig.p, B.work.p, lwork, B.info.p) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnDsyevd failed");
+    int info = 0;
+    OFLY_CUDA(cudaMemcpyAsync(&info, B.info.p, sizeof(int), cudaMemcpyDeviceToHost, b->ctx->stream));
+    OFLY_CUDA(cudaMemcpyAsync(eig_host, B.eig.p, sizeof(double) * (size_t)n3, cudaMemcpyDeviceToHost, b->ctx->stream));
+    OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    if (info != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnDsyevd did not converge (info = " + std::to_string(info) + ")");
+    b->ctx->launches += 1;
   });
 }
 

@@ -234,6 +234,12 @@ class Generic:
         check(nl.sys.ctx.lib.ofly_eam_hessian(nl.sys.h, replica, 1 if mass_weight else 0, ptr(out, _dp)))
         return out.T.copy()  # the library writes column-major
 
+    def hessian_eigenvalues(self, nl: List, replica: int = 0, mass_weight: bool = True) -> np.ndarray:
+        """system::Hessian::eigenvalues() of the (mass-weighted) Hessian, solved on the device: only 3N doubles return."""
+        out = np.zeros(3 * nl.sys.N, dtype=np.float64)
+        check(nl.sys.ctx.lib.ofly_eam_hessian_eigenvalues(nl.sys.h, replica, 1 if mass_weight else 0, ptr(out, _dp)))
+        return out
+
 
 def lbfgs_options(**kw) -> LbfgsOptions:
     o = LbfgsOptions()

@@ -173,3 +173,25 @@ def test_errors(gpu, oracle_lib):
     with pytest.raises(fly.OflyError):
         fly.System(data, fly.Box(tuple(ex)), np.full(10, 7, np.uint32))  # TypeID outside the table
     s.close()
+
+
+def test_hessian_eigenvalues_on_device(gpu, otab, oracle_lib):
+    """Hessian::eigenvalues() (hessian.hpp:86-93) solved on the device (cuSOLVER) against numpy on the oracle's Hessian:
+    3 zero modes of the vacancy-free cell (tests/potential/EAM/eam.cpp:173-183), the rest to 1e-9 absolute."""
+    fly, ctx, data = gpu
+    pos, ex, ids = golden_cell(erase=False)
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(pos)
+    pot = fly.Generic(data)
+    ev = pot.hessian_eigenvalues(nl, mass_weight=False)
+    assert np.all(np.diff(ev) > -1e-12)  # ascending (degenerate modes may swap at rounding level)
+    assert np.abs(ev[:3]).max() < 1e-10 and ev[3] > 1e-4
+    osys = oracle_lib.System(otab, ex)
+    osys.rebuild(otab.rcut, pos, 8)
+    Ho = osys.hessian(ids, np.zeros(len(ids), np.uint8), 8)
+    assert np.abs(ev - fly.hessian_eigenvalues(Ho)).max() < 1e-9
+    evm = pot.hessian_eigenvalues(nl, mass_weight=True)
+    Hm = osys.hessian(ids, np.zeros(len(ids), np.uint8), 8, mass_weight=True)
+    assert np.abs(evm - fly.hessian_eigenvalues(Hm)).max() < 1e-10
+    s.close()
