@@ -248,6 +248,9 @@ def run_b200(args):
                   "rebuild_atoms_per_s": len(id4) / (rb4 * 1e-3), "rebuild_ms": rb4}
         ctx.free(d4), ctx.free(g4)
         s4.close()
+    c3_leg = None
+    if rank == 0 and not args.no_c3:
+        c3_leg = c3_environment(ctx, data, pot, dopt, ropt, args.seed)
 
     # reduce over ranks: max time, sum of work
     if world > 1:
@@ -297,6 +300,8 @@ def run_b200(args):
         }
         if c4_leg:
             out["c4_single_system"] = c4_leg
+        if c3_leg:
+            out["c3_environment"] = c3_leg
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(rmin, ex, ids, P, A, steps=1)
         print(json.dumps(out), flush=True)
@@ -304,6 +309,51 @@ def run_b200(args):
     sysR.close(), data.close(), ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def c3_environment(ctx, data, pot, dopt, ropt, seed):
+    """BASELINE configs[2]: apps/hydrogen-sized cell (6^3 Fe - 1 vacancy + 1 H = 431 atoms), 256 dimer searches from one
+    environment, then for every saddle found the mass-weighted Hessian and its eigenvalues on the device and the Vineyard
+    prefactor (find.cpp:846-871); wall-clock, host buffers in and out."""
+    from openfly_b200 import fly, inputs
+
+    pos, ex, ids = inputs.iron_hydrogen_cell(6, 2.855, remove=(1,), hydrogen=True)
+    box = fly.Box(tuple(ex))
+    s1 = fly.System(data, box, ids)
+    rmin, _, failed, _ = fly.LBFGS().minimise(s1, pos, pot)
+    R = 256
+    P, A = inputs.perturbed_batch(rmin[0], ex, len(ids) - 1, R, seed)
+    sR = fly.System(data, box, ids, replicas=R)
+    dimer = fly.Dimer(dopt, ropt)
+    dimer.find_sp(sR, P, A, rmin[0], pot)  # warm-up (allocations, module load)
+    t0 = time.perf_counter()
+    out_r, out_ax, code, cnt = dimer.find_sp(sR, P, A, rmin[0], pot)
+    t_search = time.perf_counter() - t0
+    nl = fly.List(s1, data.rcut())
+    try:
+        nl.rebuild(rmin[0])
+        ev_min = pot.hessian_eigenvalues(nl)
+        t0 = time.perf_counter()
+        nus = []
+        for k in np.nonzero(code == 0)[0]:
+            nl.rebuild(out_r[k])
+            try:
+                nu = fly.vineyard_prefactor(ev_min, pot.hessian_eigenvalues(nl))
+            except fly.OflyError:
+                nu = None
+            if nu is not None:
+                nus.append(nu)
+        t_hess = time.perf_counter() - t0
+    except fly.OflyError as e:  # no cuSOLVER on this box
+        t_hess, nus = None, str(e)
+    n_ok = int((code == 0).sum())
+    sR.close(), s1.close()
+    return {"workload": "C3: 6^3 Fe - vacancy + H (431 atoms), 256 dimer searches of one environment + Hessian / eigenvalues / prefactor per saddle",
+            "searches": R, "saddles": n_ok, "search_s": t_search, "searches_per_s": R / t_search,
+            "atom_evals_per_s": float(cnt[:, 0].sum()) * len(ids) / t_search, "longest_search_evals": int(cnt[:, 0].max()),
+            "hessian_eigen_s": t_hess, "hessian_eigen_ms_per_saddle": (t_hess / max(n_ok, 1) * 1e3) if t_hess else None,
+            "prefactors": (len(nus) if isinstance(nus, list) else nus),
+            "median_prefactor_hz": (float(np.median(nus)) if isinstance(nus, list) and nus else None)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -409,6 +459,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1334)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 single-system leg")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 environment leg (256 searches + Hessians / prefactors)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -253,10 +253,14 @@ int ofly_ctx_create(int device, ofly_ctx **out) {
     *out = c;
   });
 }
+namespace ofly {
+  void destroy_cusolver(ofly_ctx *ctx);  // defined with the Hessian entry points
+}
 void ofly_ctx_destroy(ofly_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ofly::destroy_cusolver(ctx);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -414,6 +418,7 @@ void ofly_batch_destroy(ofly_batch *b) {
   b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release(), b->sel_all.release();
   b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();
   for (auto &buf : b->io_pool) buf.release();
+  b->hess_H.release(), b->hess_aux.release(), b->hess_mass.release(), b->hess_work.release(), b->hess_eig.release(), b->hess_info.release();
   ofly_tables_release(b->tables);
   delete b;
 }
@@ -588,10 +593,11 @@ namespace ofly {
     if (mass_weight) launch(b->ctx, k_hess_mass_weight, n3 * n3, 256, H.p, (int)b->N, (const uint8_t *)b->type.p, (const double *)mass.p);
   }
 
+  // The dense-Hessian buffers live in the batch: the Master computes one Hessian per saddle found, hundreds per batch.
   struct HessBufs {
-    DevBuf<double> H, aux, mass, work, eig;
-    DevBuf<int> info;
-    ~HessBufs() { H.release(), aux.release(), mass.release(), work.release(), eig.release(), info.release(); }
+    DevBuf<double> &H, &aux, &mass, &work, &eig;
+    DevBuf<int> &info;
+    explicit HessBufs(ofly_batch *b) : H(b->hess_H), aux(b->hess_aux), mass(b->hess_mass), work(b->hess_work), eig(b->hess_eig), info(b->hess_info) {}
   };
 
   // cuSOLVER is loaded on first use (dlopen), so the library itself carries no load-time dependency on it.
@@ -622,12 +628,16 @@ namespace ofly {
     }();
     return c;
   }
+  void destroy_cusolver(ofly_ctx *ctx) {
+    if (ctx->cusolver && cusolver().ok()) cusolver().destroy(ctx->cusolver);
+    ctx->cusolver = nullptr;
+  }
 }  // namespace ofly
 
 int ofly_eam_hessian(ofly_batch *b, long replica, int mass_weight, double *hess_host) {
   return guarded([&] {
     require(b && hess_host, "null argument");
-    HessBufs B;
+    HessBufs B(b);
     assemble_hessian(b, replica, mass_weight, B.H, B.aux, B.mass);
     size_t n3 = 3 * (size_t)b->N;
     OFLY_CUDA(cudaMemcpyAsync(hess_host, B.H.p, sizeof(double) * n3 * n3, cudaMemcpyDeviceToHost, b->ctx->stream));
@@ -640,18 +650,20 @@ int ofly_eam_hessian_eigenvalues(ofly_batch *b, long replica, int mass_weight, d
     require(b && eig_host, "null argument");
     Cusolver &cs = cusolver();
     if (!cs.ok()) throw Error(OFLY_ERR_CUDA, "libcusolver could not be loaded (needed for the dense symmetric eigenvalue solve)");
-    HessBufs B;
+    HessBufs B(b);
     assemble_hessian(b, replica, mass_weight, B.H, B.aux, B.mass);
     throw_on_fault(collect_faults(b));
     const int n3 = 3 * (int)b->N;
-    void *h = nullptr;
-    if (cs.create(&h) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnCreate failed");
-    struct Guard {
-      Cusolver &c;
-      void *h;
-      ~Guard() { c.destroy(h); }
-    } guard{cs, h};
-    if (cs.set_stream(h, b->ctx->stream) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnSetStream failed");
+    if (!b->ctx->cusolver) {  // one handle per context, bound to its stream
+      void *created = nullptr;
+      if (cs.create(&created) != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnCreate failed");
+      if (cs.set_stream(created, b->ctx->stream) != 0) {
+        cs.destroy(created);
+        throw Error(OFLY_ERR_CUDA, "cusolverDnSetStream failed");
+      }
+      b->ctx->cusolver = created;
+    }
+    void *h = b->ctx->cusolver;
     B.eig.reserve((size_t)n3), B.info.reserve(1);
     int lwork = 0;
     // jobz = CUSOLVER_EIG_MODE_NOVECTOR (0), uplo = CUBLAS_FILL_MODE_LOWER (0): the lower triangle is what system::Hessian

@@ -54,6 +54,7 @@ struct ofly_ctx {
   cudaStream_t stream = nullptr;
   long launches = 0;
   long ticks = 0;  // search ticks executed (search.cuh)
+  void *cusolver = nullptr;  // cusolverDnHandle_t, created on the first dense eigenvalue solve
   int sm_count = 0;
   int max_smem_optin = 0;
 };
@@ -84,6 +85,8 @@ struct ofly_batch {
   ofly::DevBuf<int> sel_all;  // [R + 1]: 0..R-1 then R -- the "every replica" selection of the grid kernels
   ofly::DevBuf<double> stage_a, stage_b, stage_c, scratch;  // [R][3N] staging for the host-pointer entry points
   ofly::DevBuf<char> search_ws;                              // workspace of the search engine
+  ofly::DevBuf<double> hess_H, hess_aux, hess_mass, hess_work, hess_eig;  // dense Hessian path, kept between calls
+  ofly::DevBuf<int> hess_info;
   std::vector<ofly::DevBuf<char>> io_pool;                   // device staging of the host-pointer search calls
   std::vector<int> fault_host;
 };
