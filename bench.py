@@ -16,8 +16,9 @@ vector algebra of every active replica, rebuilds, one gradient evaluation) repea
   cpu_baseline / --impl reference: the CPU oracle built with the reference's flags, all host cores, one
            single-threaded search per core exactly like saddle::Master (src/saddle/find.cpp:698,990)
 
-N > 1 (torchrun): replicas shard by rank with no collective on the data path; every rank runs its own
-64-search batch (weak scaling); only the timing and the counters are reduced.
+N > 1 (torchrun): replicas shard by rank with no collective on the data path; every rank runs a 64-search batch of its
+own device (the same start states on every rank, so that per-GPU work is fixed: weak scaling); only the timing and the
+counters are reduced.
 """
 from __future__ import annotations
 
@@ -134,7 +135,10 @@ def run_b200(args):
     assert not failed[0], "set-up minimisation did not converge"
     rmin = rmin[0]
     s1.close()
-    P, A = inputs.perturbed_batch(rmin, ex, N - 1, R, args.seed + 1000 * rank)
+    # Every rank runs the SAME 64 start states: per-GPU work is then fixed exactly, which is what weak scaling means. (With
+    # per-rank seeds a rank's step time is set by its longest search -- they vary 50x -- and the max over ranks would measure
+    # the luck of the draw: 8 independent draws gave 1.9 s for the slowest rank against 0.43 s for rank 0.)
+    P, A = inputs.perturbed_batch(rmin, ex, N - 1, R, args.seed)
 
     sysR = fly.System(data, box, ids, replicas=R)
     nbytes = P.nbytes
@@ -276,6 +280,7 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "atoms": N, "replicas_per_gpu": R,
+                       "multi_gpu": "one 64-search batch per GPU, identical start states on every rank, no data-path collective",
                        "l2": "inputs larger than L2: neighbour rows 64x16000x104x4 B = 426 MB + 1.1 GB of search vectors vs 126 MB L2; no explicit flush",
                        "seed": args.seed},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * nbytes + rmin.nbytes),

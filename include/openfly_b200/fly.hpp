@@ -242,6 +242,13 @@ namespace fly_b200 {
         detail::check(ofly_eam_hessian(nl.system().handle(), replica, mass_weight ? 1 : 0, out.data()));
       }
 
+      // system::Hessian::eigenvalues() (hessian.hpp:86-93) of that matrix, ascending, solved on the device: out [3N].
+      // What saddle::Master feeds its Vineyard prefactors with (find.cpp:846-871, 1107-1135).
+      void hessian_eigenvalues(std::span<double> out, neigh::List const &nl, long replica = 0, bool mass_weight = true) const {
+        detail::expect(out.size() == static_cast<std::size_t>(3 * nl.size()), "hessian_eigenvalues: expected 3N values");
+        detail::check(ofly_eam_hessian_eigenvalues(nl.system().handle(), replica, mass_weight ? 1 : 0, out.data()));
+      }
+
     private:
       DataEAM m_data;
     };
