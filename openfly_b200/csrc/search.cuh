@@ -9,22 +9,26 @@
 // Every algorithm above is a chain of 3N-vector passes punctuated by EAM gradient evaluations (and,
 // when the skin is used up, a neighbour rebuild). The gradient is the expensive, embarrassingly
 // parallel part, so the batch advances in *ticks*: in one tick every still-searching replica runs its
-// own vector algebra up to its next gradient request (k_segment, one team = one CTA or one cluster of
-// CTAs per replica; replicas may be at completely different places of the algorithm), then ONE set of
-// grid kernels (neigh.cuh / eam.cuh) rebuilds the lists of the replicas that asked for it and
-// evaluates the gradient of all active replicas with the whole chip. A tick is a fixed sequence of
-// eight kernel nodes; the host enqueues it as a CUDA graph whose body repeats on the device (WHILE
-// conditional node) until no replica is active -- no per-step host round trip, no host-side branch.
-// Finished replicas simply drop out of the selection lists, so the chip stays full until the last
-// search ends instead of idling behind the slowest one.
+// own vector algebra up to its next gradient request (k_segment: one team = one CTA or one cluster of
+// 2-16 CTAs per entry of the list of active replicas; replicas may be at completely different places
+// of the algorithm), then ONE set of grid kernels (neigh.cuh / eam.cuh) rebuilds the lists of the
+// replicas that asked for it and evaluates the gradient of all active replicas with the whole chip.
+// A tick is a fixed sequence of kernel nodes (segment, five rebuild kernels behind an IF node that is
+// only armed when somebody asked, two pair kernels); the host enqueues it as a CUDA graph whose body
+// repeats on the device (WHILE conditional node) until no replica is active -- no per-step host round
+// trip, no host-side branch. Finished replicas drop out of the list, so the chip stays as full as the
+// batch allows; for most ticks of a batch only a few replicas are left (search lengths vary 50x) and a
+// tick is a latency chain, which is what the choices below are made for.
 //
 // Vector algebra: every pass is strided over the team; dot products are fused into the pass that
-// produces their operand (the L-BFGS two-loop costs one pass + one reduction per history pair) and
-// reduced warp-shuffle -> shared memory -> (cluster: st.async posts into every peer's shared memory,
-// counted in by mbarriers) in a fixed order, so all threads of a team obtain bit-identical scalars and
-// take the same branches without a broadcast. Every pass is indexed by vector component, so a thread
-// only re-reads data it wrote itself and no pass needs a memory fence or a cluster barrier.
-// Per-replica scalars (phase, trust, acc, curvature, L-BFGS rho_j, counters) persist in RepState.
+// produces their operand and reduced warp-shuffle -> shared memory -> (cluster: st.async posts into
+// every peer's shared memory, counted in by mbarriers) in a fixed order, so all threads of a team
+// obtain bit-identical scalars and take the same branches without a broadcast. Every pass is indexed
+// by vector component, so a thread only re-reads data it wrote itself and no pass needs a memory fence
+// or a cluster barrier. The L-BFGS step takes two passes and two reductions whatever the history
+// length (newton_step_gram); transcendental scalars are computed by one warp and shared.
+// Per-replica scalars (phase, trust, acc, curvature, L-BFGS rho_j and Gram entries, counters) persist
+// in RepState. OFLY_TRACE=<replica> records time stamps inside the kernels (trace_mark).
 #pragma once
 
 #include <cooperative_groups.h>
