@@ -1,0 +1,10 @@
+# Final round-1 validation of the committed tree: build check, GPU tests, smoke, default bench (both arms).
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem --format=csv,noheader
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/r2g_bench.json 2> gpurun_out/r2g_bench.err
+tail -c 300 gpurun_out/r2g_bench.err
+timeout 900 python bench.py --impl reference > gpurun_out/r2g_bench_reference.json 2>> gpurun_out/r2g_bench.err
+for f in gpurun_out/r2g_bench.json gpurun_out/r2g_bench_reference.json; do python -c "
+import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print({k:d.get(k) for k in ['impl','value','ms_per_step','ticks_per_step','dimer_searches_per_s','gpu_launches']}, d['e2e']['value'], d.get('roofline',{}).get('frac'), d.get('cpu_baseline',{}).get('value'), d.get('cpu_baseline',{}).get('cores'), d.get('clocks'))"; done
