@@ -42,8 +42,8 @@ METRIC, UNIT = "eam_atom_gradient_evals_per_s", "atom-evals/s"
 WORKLOAD = "C2: bcc Fe 20^3 (a=2.8553) - 1 vacancy + 1 H = 16000 atoms, Wen Fe-H EAM, 64 concurrent dimer searches (Dimer::find_sp, default options)"
 CPU_SAMPLE_MAX_STEPS = 40  # translation steps per CPU search in the bounded sample
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_rho<4> + k_eam_force<4> launch pair on this workload, from the
-# ncu --set full capture profiles/r1n_eam_pair.txt: (403.1 + 31.1) + (404.0 + 23.5) MB
-NCU_TRAFFIC = 861.7e6
+# ncu --set full capture profiles/r2h_eam_pair.txt: (403.1 + 29.3) + (404.1 + 24.0) MB
+NCU_TRAFFIC = 860.4e6
 
 
 def peaks():
