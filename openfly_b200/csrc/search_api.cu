@@ -1,5 +1,6 @@
 // C ABI: minimise::LBFGS::minimise and saddle::Dimer::find_sp over a whole batch (search.cuh).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -81,11 +82,12 @@ namespace ofly {
       attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = C > 1 ? 1 : 0;
-      if (C > 8) {
-        static bool allowed = false;  // per instantiation
-        if (!allowed) {
+      if (C > 8) {  // non-portable cluster size: allowed per function AND per device
+        static std::atomic<unsigned long long> allowed{0};
+        const unsigned long long bit = 1ull << (ctx->device & 63);
+        if (!(allowed.load() & bit)) {
           OFLY_CUDA(cudaFuncSetAttribute(k_segment<C, MAXT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-          allowed = true;
+          allowed.fetch_or(bit);
         }
       }
       OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT>, B, P));

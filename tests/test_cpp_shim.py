@@ -11,6 +11,7 @@ import pytest
 from tests.common import ROOT, WEN, bcc_vacancy
 
 DEMO = os.path.join(ROOT, "examples", "shim_demo")
+MGPU = os.path.join(ROOT, "examples", "multi_gpu_batch")
 
 
 @pytest.fixture(scope="module")
@@ -69,3 +70,34 @@ def test_shim_demo_matches_oracle(demo, oracle_lib, tmp_path):
     for k in range(R):
         if o_code[k] == 0:
             assert np.abs(sp[k] - o_r[k]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_cpp_host_shards_replicas_over_devices(demo, oracle_lib, tmp_path):
+    """examples/multi_gpu_batch.cpp: one host thread + Context per device, replica r on device r mod G, merge in replica
+    order. With every visible device (one is enough to run it) the merged result equals the single-device one."""
+    import torch
+
+    cells, R = 4, 6
+    base, ex, ids = bcc_vacancy(cells, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    tab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(tab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=4)
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(R)]
+    path = tmp_path / "starts.bin"
+    np.stack([np.stack([s[0], s[1]]) for s in starts]).astype(np.float64).tofile(path)
+    runs = {}
+    for g in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        out = subprocess.run([MGPU, WEN, str(cells), str(R), str(path), str(g)], check=True, capture_output=True, text=True).stdout
+        d = json.loads(out)
+        assert d["devices"] == g and d["replicas"] == R
+        runs[g] = (d["exits"], np.fromfile(str(path) + ".mgpu", dtype=np.float64))
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    o_r, _, o_code, _ = osys.find_sp_batch(P, A, ids, fz, r0, threads=4)
+    for g, (exits, sp) in runs.items():
+        assert exits == o_code.tolist()
+        sp = sp.reshape(R, -1, 3)
+        for k in range(R):
+            if o_code[k] == 0:
+                assert np.abs(sp[k] - o_r[k]).max() < 1e-5
