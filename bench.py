@@ -254,7 +254,7 @@ def run_b200(args):
         s4.close()
     c3_leg = None
     if rank == 0 and not args.no_c3:
-        c3_leg = c3_environment(ctx, data, pot, dopt, ropt, args.seed)
+        c3_leg = c3_environment(ctx, data, pot, dopt, ropt, args.seed, 2048 // world)
 
     # reduce over ranks: max time, sum of work
     if world > 1:
@@ -316,7 +316,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def c3_environment(ctx, data, pot, dopt, ropt, seed):
+def c3_environment(ctx, data, pot, dopt, ropt, seed, c5_replicas):
     """BASELINE configs[2]: apps/hydrogen-sized cell (6^3 Fe - 1 vacancy + 1 H = 431 atoms), 256 dimer searches from one
     environment, then for every saddle found the mass-weighted Hessian and its eigenvalues on the device and the Vineyard
     prefactor (find.cpp:846-871); wall-clock, host buffers in and out."""
@@ -353,7 +353,19 @@ def c3_environment(ctx, data, pot, dopt, ropt, seed):
         t_hess, nus = None, str(e)
     n_ok = int((code == 0).sum())
     sR.close(), s1.close()
-    return {"workload": "C3: 6^3 Fe - vacancy + H (431 atoms), 256 dimer searches of one environment + Hessian / eigenvalues / prefactor per saddle",
+    # C5: this rank's shard of 2048 concurrent searches on the same cell (replica r -> rank r mod world: 2048 / world here)
+    P5, A5 = inputs.perturbed_batch(rmin[0], ex, len(ids) - 1, c5_replicas, seed + 7)
+    s5 = fly.System(data, box, ids, replicas=c5_replicas)
+    dimer.find_sp(s5, P5, A5, rmin[0], pot)
+    t0 = time.perf_counter()
+    _, _, code5, cnt5 = dimer.find_sp(s5, P5, A5, rmin[0], pot)
+    t5 = time.perf_counter() - t0
+    s5.close()
+    c5 = {"workload": "C5: shard of 2048 concurrent searches on the 431-atom cell (2048 / n_gpus replicas on this rank)",
+          "replicas": c5_replicas, "search_s": t5, "searches_per_s": c5_replicas / t5,
+          "atom_evals_per_s": float(cnt5[:, 0].sum()) * len(ids) / t5, "longest_search_evals": int(cnt5[:, 0].max()),
+          "mean_search_evals": float(cnt5[:, 0].mean()), "saddles": int((code5 == 0).sum())}
+    return {"c5_shard": c5,"workload": "C3: 6^3 Fe - vacancy + H (431 atoms), 256 dimer searches of one environment + Hessian / eigenvalues / prefactor per saddle",
             "searches": R, "saddles": n_ok, "search_s": t_search, "searches_per_s": R / t_search,
             "atom_evals_per_s": float(cnt[:, 0].sum()) * len(ids) / t_search, "longest_search_evals": int(cnt[:, 0].max()),
             "hessian_eigen_s": t_hess, "hessian_eigen_ms_per_saddle": (t_hess / max(n_ok, 1) * 1e3) if t_hess else None,
