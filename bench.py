@@ -418,9 +418,20 @@ def cpu_baseline(rmin, ex, ids, P, A, steps: int):
         dt = time.perf_counter() - t0
         v = float(cnt[:, 0].sum()) * len(ids) / dt
         best = v if best is None else max(best, v)
+    # the same kernels as the roofline pair, CPU side: update + gradient of ONE C2 system with every core inside the call,
+    # exactly as EAM::gradient(..., threads) is used (eam.cpp:81,115); list at the dimer's radius
+    r_list = 5.3 + 0.002
+    r_list += (1.1 ** (1 / 3) - 1) * r_list
+    osys.rebuild(r_list, P[0], cores)
+    delta = np.random.default_rng(0).normal(0, 1e-3, P[0].shape)
+    osys.time_gradient(ids, fz, delta, cores, 2)
+    iters = 20
+    g_s = osys.time_gradient(ids, fz, delta, cores, iters)
     return {"value": best, "unit": UNIT, "cores": int(cores), "kind": "port",
             "sample": f"{n} of the 64 C2 searches (one single-threaded search per core, as saddle::Master), each cut at "
-                      f"max_steps={CPU_SAMPLE_MAX_STEPS}; oracle flags: {flags}"}
+                      f"max_steps={CPU_SAMPLE_MAX_STEPS}; oracle flags: {flags}",
+            "gradient_only": {"atom_evals_per_s": len(ids) * iters / g_s, "ms_per_eval": g_s / iters * 1e3, "threads": int(cores),
+                              "what": "List::update + EAM::gradient of one 16 000-atom system, all cores inside the call"}}
 
 
 def run_reference(args):
