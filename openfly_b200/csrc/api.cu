@@ -195,7 +195,7 @@ namespace ofly {
     Sel all = all_replicas(b);
     const size_t stride = (size_t)3 * b->N;
     const int G = pick_group(ctx, (long)atoms);
-    const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), 8);
+    const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), env_int("OFLY_PAIR_CTAS", 32));
     switch (G) {
       case 32:
         k_eam_rho<32><<<gg, 256, 0, st>>>(b->d, T, all);

@@ -137,7 +137,7 @@ namespace ofly {
       if (!(forced == 4 || forced == 8 || forced == 16 || forced == 32)) forced = 0;
       const int G = forced ? forced : 32;
       const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
-      return {forced, stride_grid(b->ctx, tiles, 8), (long)b->ctx->sm_count * 2048};
+      return {forced, stride_grid(b->ctx, tiles, env_int("OFLY_PAIR_CTAS", 32)), (long)b->ctx->sm_count * 2048};
     }
 
     void enqueue_rebuild(ofly_batch *b, SearchParams const &P) {
