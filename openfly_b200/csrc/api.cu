@@ -143,7 +143,8 @@ namespace ofly {
     k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(b->d, all);
     k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(b->d, all);
     k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * b->d.grid.ncells + 127) / 128, 16), 128, 0, st>>>(b->d, all);
-    const int G = pick_group(ctx, (long)atoms);
+    int G = env_int("OFLY_GROUP", 0);  // tuning override; the rows do not depend on the width
+    if (!(G == 4 || G == 8 || G == 16 || G == 32)) G = build_group_for((long)atoms, (long)ctx->sm_count * 2048);
     const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), 8);
     switch (G) {
       case 32:

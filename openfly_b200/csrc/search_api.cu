@@ -165,9 +165,7 @@ namespace ofly {
           k_nb_build<4><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
         default:
-          // the build is bound by instruction issue, not by the gather path: its best width differs from the pair kernels'
-          // (OFLY_BUILD_WAVES scales the resident-thread budget the rule of k_nb_build_dyn sees; measured on C2: 432.7 ms per step at 1, 426.2 at 8)
-          k_nb_build_dyn<<<pg.blocks, 256, 0, st>>>(B, reb, pg.slots * std::max(1, env_int("OFLY_BUILD_WAVES", 8)));
+          k_nb_build_dyn<<<pg.blocks, 256, 0, st>>>(B, reb, pg.slots);
           break;
       }
       OFLY_CUDA(cudaGetLastError());
