@@ -165,7 +165,7 @@ namespace ofly {
           k_nb_build<4><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
         default:
-          k_nb_build_dyn<<<pg.blocks, 256, 0, st>>>(B, reb, pg.slots);
+          k_nb_build_dyn<<<pg.blocks, 256, 0, st>>>(B, reb, 4 * pg.slots);  // budget: four waves of resident threads
           break;
       }
       OFLY_CUDA(cudaGetLastError());
