@@ -53,6 +53,7 @@ const char *ofly_last_error(void);
 const char *ofly_version(void);
 
 int ofly_ctx_create(int device, ofly_ctx **out);
+/* Destroy every batch and release every table handle made on a context before the context itself. */
 void ofly_ctx_destroy(ofly_ctx *ctx);
 /* The context's cudaStream_t (so a caller can time it with events or order work after it). */
 void *ofly_ctx_stream(ofly_ctx *ctx);
