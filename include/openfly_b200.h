@@ -68,6 +68,19 @@ long ofly_ctx_tick_count(ofly_ctx *ctx);
 /* Parse a LAMMPS setfl eam/fs file and build the natural cubic splines (data.cpp:67-153,
  * src/utility/spline.cpp:27-103), then upload the knots. */
 int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out);
+/* The same from memory: DataEAM(std::istream&) (data.cpp:67) for hosts that hold the file's text. */
+int ofly_tables_load_setfl_mem(ofly_ctx *ctx, const char *text, size_t len, ofly_tables **out);
+/* From already-splined knots (a host that owns a fly::potential::DataEAM hands its Spline coefficients over):
+ * names/mass: [n_types]; F_abcd: [n_types][n_knots_F][4] = {a,b,c,d} (spline.hpp:121-126); phi_abcd: [src + n*dst][n_knots_r][4]
+ * (data.hpp:109-112); V_abcd: [max + n*min][n_knots_r][4] (data.hpp:114-116, unused slots ignored). */
+int ofly_tables_create_from_knots(ofly_ctx *ctx, int n_types, const char *const *names, const double *mass, long n_knots_F, double d_rho,
+                                  long n_knots_r, double d_r, double r_cut, const double *F_abcd, const double *phi_abcd,
+                                  const double *V_abcd, ofly_tables **out);
+/* Name of type i as the table declares it (line 4 of the setfl file); NULL if out of range. */
+const char *ofly_tables_type_name(const ofly_tables *t, int i);
+/* EAM's constructor check (include/libfly/potential/EAM/eam.hpp:50-63): the caller's TypeMap must have at least the table's
+ * types, with the same names at the same ids. OFLY_ERR_INVALID with the reference's message otherwise. */
+int ofly_eam_check_type_map(const ofly_tables *t, int n_types, const char *const *names);
 void ofly_tables_retain(ofly_tables *t);
 void ofly_tables_release(ofly_tables *t);
 /* info = {n_types, n_knots_F, n_knots_r}; dinfo = {d_rho, d_r, r_cut, mass[0..n_types)} */
@@ -188,6 +201,29 @@ int ofly_dimer_find_sp_dev(ofly_batch *b, const ofly_dimer_options *opt, const o
                            const double *axis_in_dev, const double *in_min_dev, const double *hist_sp_dev, long n_hist,
                            double theta_tol, int count_frozen, double *pos_out_dev, double *axis_out_dev, int *exit_code_dev,
                            long *counters_dev);
+
+/* Queue forms of the two calls above: n_searches start states run through the batch's R resident slots. A slot whose
+ * search has finished claims the next start state on the device, inside the same graph launch, so the GPU stays full
+ * until the queue is empty -- saddle::Master::find_n's `while (tot < max_searches)` loop (src/saddle/find.cpp:374-422)
+ * without a barrier after every batch. All per-search arrays are [n_searches][...] and indexed by search; in_min and
+ * hist_sp are shared by the whole queue (the SP cache is read-only during a call, find.cpp:732-752). What a search
+ * returns does not depend on n_searches, on R, or on which searches share the device with it. n_searches == R is
+ * exactly ofly_lbfgs_minimise / ofly_dimer_find_sp. */
+int ofly_lbfgs_minimise_stream(ofly_batch *b, const ofly_lbfgs_options *opt, long n_searches, const double *pos_in_host,
+                               double *pos_out_host, double *grad_out_host, int *status_host, long *counters_host);
+int ofly_lbfgs_minimise_stream_dev(ofly_batch *b, const ofly_lbfgs_options *opt, long n_searches, const double *pos_in_dev,
+                                   double *pos_out_dev, double *grad_out_dev, int *status_dev, long *counters_dev);
+int ofly_dimer_find_sp_stream(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, long n_searches,
+                              const double *pos_in_host, const double *axis_in_host, const double *in_min_host,
+                              const double *hist_sp_host, long n_hist, double theta_tol, int count_frozen, double *pos_out_host,
+                              double *axis_out_host, int *exit_code_host, long *counters_host);
+int ofly_dimer_find_sp_stream_dev(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, long n_searches,
+                                  const double *pos_in_dev, const double *axis_in_dev, const double *in_min_dev,
+                                  const double *hist_sp_dev, long n_hist, double theta_tol, int count_frozen, double *pos_out_dev,
+                                  double *axis_out_dev, int *exit_code_dev, long *counters_dev);
+
+/* Measurement aid (bench.py): FP64 FMA instructions per second this device sustains on register-only chains. */
+int ofly_bench_fp64_fma(ofly_ctx *ctx, int iters, double *fma_per_s);
 
 /* Plain device allocation helpers so a host program needs no CUDA headers of its own. */
 int ofly_dev_alloc(ofly_ctx *ctx, size_t bytes, void **out_dev);

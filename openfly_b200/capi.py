@@ -65,6 +65,11 @@ SIGNATURES = {
     "ofly_ctx_launch_count": (C.c_long, [_vp]),
     "ofly_ctx_tick_count": (C.c_long, [_vp]),
     "ofly_tables_load_setfl": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "ofly_tables_load_setfl_mem": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
+    "ofly_tables_create_from_knots": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_char_p), _dp, C.c_long, C.c_double, C.c_long, C.c_double,
+                                                C.c_double, _dp, _dp, _dp, C.POINTER(_vp)]),
+    "ofly_tables_type_name": (C.c_char_p, [_vp, C.c_int]),
+    "ofly_eam_check_type_map": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_char_p)]),
     "ofly_tables_retain": (None, [_vp]),
     "ofly_tables_release": (None, [_vp]),
     "ofly_tables_info": (C.c_int, [_vp, _lp, _dp]),
@@ -97,7 +102,14 @@ SIGNATURES = {
                                      C.c_double, C.c_int, _dp, _dp, _ip, _lp]),
     "ofly_dimer_find_sp_dev": (C.c_int, [_vp, C.POINTER(DimerOptions), C.POINTER(RotorOptions), _vp, _vp, _vp, _vp, C.c_long,
                                          C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
+    "ofly_lbfgs_minimise_stream": (C.c_int, [_vp, C.POINTER(LbfgsOptions), C.c_long, _dp, _dp, _dp, _ip, _lp]),
+    "ofly_lbfgs_minimise_stream_dev": (C.c_int, [_vp, C.POINTER(LbfgsOptions), C.c_long, _vp, _vp, _vp, _vp, _vp]),
+    "ofly_dimer_find_sp_stream": (C.c_int, [_vp, C.POINTER(DimerOptions), C.POINTER(RotorOptions), C.c_long, _dp, _dp, _dp, _dp,
+                                            C.c_long, C.c_double, C.c_int, _dp, _dp, _ip, _lp]),
+    "ofly_dimer_find_sp_stream_dev": (C.c_int, [_vp, C.POINTER(DimerOptions), C.POINTER(RotorOptions), C.c_long, _vp, _vp, _vp, _vp,
+                                                C.c_long, C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
     "ofly_eam_hessian_eigenvalues": (C.c_int, [_vp, C.c_long, C.c_int, _dp]),
+    "ofly_bench_fp64_fma": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "ofly_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "ofly_dev_free": (C.c_int, [_vp, _vp]),
     "ofly_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <sstream>
 
 #include "eam.cuh"
 #include "hessian.cuh"
@@ -47,16 +48,15 @@ namespace ofly {
     return v ? std::atoi(v) : dflt;
   }
 
-  // Lanes per atom for the sub-warp kernels: few atoms -> wide groups (more threads in flight),
-  // many atoms -> narrow groups (fewer idle lanes on the ragged row tail).
+  // Lanes per atom for the pair kernels: few atoms -> wide groups (more threads in flight), many atoms -> narrow
+  // groups (fewer idle lanes on the ragged row tail). The sums do not depend on it (eam.cuh, VirtSum).
   int pick_group(ofly_ctx *ctx, long atoms) {
     int forced = env_int("OFLY_GROUP", 0);
-    if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    if (forced == 4 || forced == 8 || forced == 16) return forced;
     long slots = (long)ctx->sm_count * 2048;
     if (atoms * 4 >= 2 * slots) return 4;
     if (atoms * 8 >= 2 * slots) return 8;
-    if (atoms * 16 >= slots) return 16;
-    return 32;
+    return 16;
   }
 
   template <typename K, typename... A>
@@ -198,10 +198,6 @@ namespace ofly {
     const int G = pick_group(ctx, (long)atoms);
     const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), env_int("OFLY_PAIR_CTAS", 32));
     switch (G) {
-      case 32:
-        k_eam_rho<32><<<gg, 256, 0, st>>>(b->d, T, all);
-        k_eam_force<32><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
-        break;
       case 16:
         k_eam_rho<16><<<gg, 256, 0, st>>>(b->d, T, all);
         k_eam_force<16><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
@@ -212,7 +208,11 @@ namespace ofly {
         break;
       default:
         k_eam_rho<4><<<gg, 256, 0, st>>>(b->d, T, all);
-        k_eam_force<4><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
+        if (env_int("OFLY_FORCE_MINB", 4) == 3) {  // tuning: uncapped registers (80), three CTAs per SM
+          k_eam_force<4, 3><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
+        } else {
+          k_eam_force<4><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
+        }
         break;
     }
     ctx->launches += 2;
@@ -276,14 +276,13 @@ long ofly_ctx_launch_count(ofly_ctx *ctx) { return ctx ? ctx->launches : 0; }
 long ofly_ctx_tick_count(ofly_ctx *ctx) { return ctx ? ctx->ticks : 0; }
 
 // ---- tables ------------------------------------------------------------------------------------
-int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out) {
-  return guarded([&] {
-    require(ctx && path && out, "null argument");
-    use(ctx);
+namespace ofly {
+  // Upload host tables and fill the device descriptor.
+  static ofly_tables *upload_tables(ofly_ctx *ctx, HostTables &&host) {
     auto *t = new ofly_tables;
     try {
       t->ctx = ctx;
-      t->host = read_setfl(path);
+      t->host = std::move(host);
       HostTables const &h = t->host;
       static_assert(sizeof(Knot) == sizeof(double4), "knot layout");
       t->F.reserve(h.F.size()), t->phi.reserve(h.phi.size()), t->V.reserve(h.V.size());
@@ -299,7 +298,67 @@ int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out) {
       delete t;
       throw;
     }
-    *out = t;
+    return t;
+  }
+}  // namespace ofly
+
+int ofly_tables_load_setfl(ofly_ctx *ctx, const char *path, ofly_tables **out) {
+  return guarded([&] {
+    require(ctx && path && out, "null argument");
+    use(ctx);
+    *out = upload_tables(ctx, read_setfl(std::string(path)));
+  });
+}
+int ofly_tables_load_setfl_mem(ofly_ctx *ctx, const char *text, size_t len, ofly_tables **out) {
+  return guarded([&] {
+    require(ctx && text && out, "null argument");
+    use(ctx);
+    std::istringstream in(std::string(text, len));
+    *out = upload_tables(ctx, read_setfl(in));
+  });
+}
+int ofly_tables_create_from_knots(ofly_ctx *ctx, int n_types, const char *const *names, const double *mass, long n_knots_F, double d_rho,
+                                  long n_knots_r, double d_r, double r_cut, const double *F_abcd, const double *phi_abcd,
+                                  const double *V_abcd, ofly_tables **out) {
+  return guarded([&] {
+    require(ctx && names && mass && F_abcd && phi_abcd && V_abcd && out, "null argument");
+    require(n_types >= 1 && n_types <= kMaxTypes, "unsupported number of types");
+    require(n_knots_F >= 1 && n_knots_r >= 1 && d_rho > 0 && d_r > 0 && r_cut > 0, "bad tabulation");
+    use(ctx);
+    HostTables h;
+    const size_t n = (size_t)n_types;
+    h.n_types = n_types, h.knots_rho = n_knots_F, h.knots_r = n_knots_r;
+    h.n_rho = n_knots_F - 4, h.n_r = n_knots_r - 4;
+    h.d_rho = d_rho, h.d_r = d_r, h.r_cut = r_cut;
+    for (size_t i = 0; i < n; i++) {
+      require(names[i] != nullptr, "null type name");
+      h.names.emplace_back(names[i]), h.mass.push_back(mass[i]);
+    }
+    static_assert(sizeof(Knot) == 4 * sizeof(double), "knot layout");
+    h.F.resize(n * (size_t)n_knots_F), h.phi.resize(n * n * (size_t)n_knots_r), h.V.resize(n * n * (size_t)n_knots_r);
+    std::memcpy(h.F.data(), F_abcd, h.F.size() * sizeof(Knot));
+    std::memcpy(h.phi.data(), phi_abcd, h.phi.size() * sizeof(Knot));
+    std::memcpy(h.V.data(), V_abcd, h.V.size() * sizeof(Knot));
+    *out = upload_tables(ctx, std::move(h));
+  });
+}
+const char *ofly_tables_type_name(const ofly_tables *t, int i) {
+  if (!t || i < 0 || i >= t->host.n_types) return nullptr;
+  return t->host.names[(size_t)i].c_str();
+}
+int ofly_eam_check_type_map(const ofly_tables *t, int n_types, const char *const *names) {
+  return guarded([&] {
+    require(t && names, "null argument");
+    const int need = t->host.n_types;
+    if (n_types < need) {
+      throw Error(OFLY_ERR_INVALID, "Not enough types in eam data file: " + std::to_string(n_types) + " < " + std::to_string(need));
+    }
+    for (int i = 0; i < need; i++) {
+      require(names[i] != nullptr, "null type name");
+      if (t->host.names[(size_t)i] != names[i]) {
+        throw Error(OFLY_ERR_INVALID, "TypeID mismatch: expecting type " + t->host.names[(size_t)i] + ", got " + names[i] + " at id=" + std::to_string(i));
+      }
+    }
   });
 }
 void ofly_tables_retain(ofly_tables *t) {
@@ -415,6 +474,7 @@ void ofly_batch_destroy(ofly_batch *b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
+  b->search_graph.reset();
   b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->cell_items.release();
   b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release(), b->sel_all.release();
   b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();
@@ -555,9 +615,6 @@ int ofly_eam_energy(ofly_batch *b, double *energy_host) {
     clear_faults(b);
     TablesDev const &T = b->tables->dev;
     switch (pick_group(b->ctx, (long)atoms)) {
-      case 32:
-        launch(b->ctx, k_eam_energy_atoms<32>, atoms * 32, 256, b->d, T, b->scratch.p);
-        break;
       case 16:
         launch(b->ctx, k_eam_energy_atoms<16>, atoms * 16, 256, b->d, T, b->scratch.p);
         break;
@@ -678,6 +735,53 @@ int ofly_eam_hessian_eigenvalues(ofly_batch *b, long replica, int mass_weight, d
     OFLY_CUDA(cudaStreamSynchronize(b->ctx->stream));
     if (info != 0) throw Error(OFLY_ERR_CUDA, "cusolverDnDsyevd did not converge (info = " + std::to_string(info) + ")");
     b->ctx->launches += 1;
+  });
+}
+
+// ---- measurement aid: achievable FP64 FMA rate (the co-limiter of the pair kernels) ---------
+namespace ofly {
+  // 8 independent FMA chains per thread, registers only: DFMA issue rate of the whole chip.
+  static __global__ void __launch_bounds__(256) k_fp64_fma(int iters, double seed, double *sink) {
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = seed + (double)(threadIdx.x + q);
+    const double m = 1.0 - 1e-9, c = 1e-9;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = fma(a[q], m, c);
+      }
+    }
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += a[q];
+    if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
+  }
+}  // namespace ofly
+
+int ofly_bench_fp64_fma(ofly_ctx *ctx, int iters, double *fma_per_s) {
+  return guarded([&] {
+    require(ctx && fma_per_s && iters > 0, "bad argument");
+    use(ctx);
+    DevBuf<double> sink;
+    sink.reserve(1);
+    const unsigned grid = (unsigned)ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    OFLY_CUDA(cudaEventCreate(&e0));
+    OFLY_CUDA(cudaEventCreate(&e1));
+    k_fp64_fma<<<grid, 256, 0, ctx->stream>>>(iters / 8 + 1, 1.0, sink.p);  // warm-up
+    OFLY_CUDA(cudaEventRecord(e0, ctx->stream));
+    k_fp64_fma<<<grid, 256, 0, ctx->stream>>>(iters, 1.0, sink.p);
+    OFLY_CUDA(cudaEventRecord(e1, ctx->stream));
+    OFLY_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    OFLY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    sink.release();
+    ctx->launches += 2;
+    *fma_per_s = (double)grid * 256.0 * 32.0 * (double)iters / ((double)ms * 1e-3);
   });
 }
 

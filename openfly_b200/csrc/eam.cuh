@@ -23,6 +23,14 @@ namespace ofly {
     int j, tj;
   };
 
+  // Row entries are a pure stream (read once per pass, 0.4 GB per pass at C2): evict-first in L2 so that the 33 MB of
+  // position records and the 2.9 MB of tables, which every SM gathers from, stay resident.
+  __device__ __forceinline__ uint32_t ld_row(const uint32_t *p) {
+    uint32_t v;
+    asm("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+  }
+
   // Decode one neighbour entry and fetch its record.
   __device__ __forceinline__ PairGeom load_pair(const BatchDev &B, const double4 *__restrict__ pos, const double4 &pi, uint32_t e) {
     PairGeom g;
@@ -44,11 +52,17 @@ namespace ofly {
   }
 
   // Spline::fetch (spline.hpp:135-154): interval index and offset. Flags OutOfBounds, clamps the read.
+  // The reference converts x * inv_dx with static_cast<size_t>: -1 < s < 0 truncates to interval 0 (no throw), s <= -1
+  // and NaN become a huge index and throw, s >= n_knots throws. The range test is done on the double so that neither a
+  // negative nor a NaN argument can index outside the table.
   __device__ __forceinline__ int knot_index(double x, double inv_dx, double dx, int n_knots, double &x0, bool &oob) {
-    int i = __double2int_rz(x * inv_dx);
-    if (i >= n_knots) {
+    const double s = x * inv_dx;
+    int i = 0;
+    if (s > -1.0 && s < (double)n_knots) {
+      i = __double2int_rz(s);
+    } else {
       oob = true;
-      i = n_knots - 1;
+      i = s > 0.0 ? n_knots - 1 : 0;  // NaN lands on 0
     }
     x0 = fma(-(double)i, dx, x);
     return i;
@@ -57,8 +71,45 @@ namespace ofly {
   __device__ __forceinline__ double spline_fp(const double4 &k, double x0) { return fma(x0, fma(x0 * 3.0, k.w, 2.0 * k.z), k.y); }
   __device__ __forceinline__ double spline_fpp(const double4 &k, double x0) { return fma(6.0 * x0, k.w, 2.0 * k.z); }
 
-  // Pass 1 for atom i by a sub-warp of G lanes: returns rho_i on every lane. If `v_sum` is non-null
-  // also accumulates sum_a V(r) (energy, eam.cpp:41-46).
+  // ---- per-atom sums whose bits do not depend on the sub-warp width ---------------------------------
+  // Entry k of an atom's row belongs to *virtual lane* k % kVirt; a virtual lane adds its terms in ascending k, and the
+  // kVirt partial sums are combined by the butterfly (v, v^8), (v, v^4), (v, v^2), (v, v^1). A physical sub-warp of
+  // G <= kVirt lanes carries kVirt / G virtual lanes per thread (lane l owns v = l + G j, one accumulator each: the same
+  // entries k = l (mod G) a plain strided loop would give it), folds the upper butterfly levels in registers and does
+  // the remaining ones with shuffles. Every G therefore produces the SAME bits, so a replica's energies, forces and
+  // trajectory do not depend on how many replicas share its batch (the tick kernels pick G from the active count) or on
+  // how a batch is sharded over GPUs.
+  constexpr int kVirt = 16;
+
+  template <int G, int NS>
+  struct VirtSum {
+    static_assert(G == 4 || G == 8 || G == 16, "sub-warp width must divide the virtual width");
+    static constexpr int J = kVirt / G;
+    double a[J][NS];
+    __device__ __forceinline__ VirtSum() {
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+#pragma unroll
+        for (int q = 0; q < NS; q++) a[j][q] = 0.0;
+      }
+    }
+    // Totals on every lane of the sub-warp.
+    __device__ __forceinline__ void total(double (&out)[NS]) {
+#pragma unroll
+      for (int h = J / 2; h >= 1; h >>= 1) {  // butterfly levels G*h = 8, 4 (those that stay inside a thread)
+#pragma unroll
+        for (int j = 0; j < h; j++) {
+#pragma unroll
+          for (int q = 0; q < NS; q++) a[j][q] = a[j][q] + a[j + h][q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NS; q++) out[q] = group_sum<G>(a[0][q]);  // levels G/2 ... 1
+    }
+  };
+
+  // Pass 1 for atom i by a sub-warp of G lanes: returns rho_i on every lane. If WITH_V, also accumulates
+  // sum_a V(r) (energy, eam.cpp:41-46) into *v_sum.
   template <int G, bool WITH_V>
   __device__ __forceinline__ double eam_rho_atom(const BatchDev &B, const TablesDev &T, int r, int i, int lane, double *v_sum, bool &oob) {
     const double4 *pos = B.pos4 + (size_t)r * B.N;
@@ -66,22 +117,30 @@ namespace ofly {
     const int n = B.cnt[(size_t)r * B.N + i];
     const int ti = B.type[i];
     const double4 pi = ld256(pos + i);
-    double rho = 0, vs = 0;
-    for (int k = lane; k < n; k += G) {
-      PairGeom g = load_pair(B, pos, pi, row[k]);
-      if (g.r2 < T.r_cut_sq) {
-        double rr = g.r2 * fast_rsqrt(g.r2);
-        double x0;
-        int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
-        rho += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
-        if (WITH_V) {
-          int hi = max(ti, g.tj), lo = min(ti, g.tj);
-          vs += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+    VirtSum<G, WITH_V ? 2 : 1> acc;
+    for (int k0 = 0; k0 < n; k0 += kVirt) {
+#pragma unroll
+      for (int j = 0; j < kVirt / G; j++) {
+        const int k = k0 + lane + G * j;
+        if (k < n) {
+          PairGeom g = load_pair(B, pos, pi, ld_row(row + k));
+          if (g.r2 < T.r_cut_sq) {
+            double rr = g.r2 * fast_rsqrt(g.r2);
+            double x0;
+            int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
+            acc.a[j][0] += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
+            if (WITH_V) {
+              int hi = max(ti, g.tj), lo = min(ti, g.tj);
+              acc.a[j][1] += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+            }
+          }
         }
       }
     }
-    if (WITH_V) *v_sum = group_sum<G>(vs);
-    return group_sum<G>(rho);
+    double tot[WITH_V ? 2 : 1];
+    acc.total(tot);
+    if (WITH_V) *v_sum = tot[WITH_V ? 1 : 0];
+    return tot[0];
   }
 
   // Pass 2 for atom i: gradient on every lane.
@@ -94,26 +153,34 @@ namespace ofly {
     const int ti = B.type[i];
     const double4 pi = ld256(pos + i);
     const double Fi = pi.w;
-    double ax = 0, ay = 0, az = 0;
-    for (int k = lane; k < n; k += G) {
-      PairGeom g = load_pair(B, pos, pi, row[k]);
-      if (g.r2 < T.r_cut_sq) {
-        double rinv = fast_rsqrt(g.r2);
-        double rr = g.r2 * rinv;
-        double x0;
-        int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
-        int hi = max(ti, g.tj), lo = min(ti, g.tj);
-        double mag = spline_fp(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
-        double p_ji = spline_fp(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);  // phi(a -> g)
-        double p_ij = p_ji;
-        if (g.tj != ti) p_ij = spline_fp(ld256_nc(T.phi + (size_t)(ti + T.n_types * g.tj) * T.kR + idx), x0);  // phi(g -> a)
-        mag = fma(Fi, p_ji, mag);
-        mag = fma(g.fprime_j, p_ij, mag);
-        double s = mag * rinv;
-        ax = fma(-s, g.dx, ax), ay = fma(-s, g.dy, ay), az = fma(-s, g.dz, az);
+    VirtSum<G, 3> acc;
+    for (int k0 = 0; k0 < n; k0 += kVirt) {
+#pragma unroll
+      for (int j = 0; j < kVirt / G; j++) {
+        const int k = k0 + lane + G * j;
+        if (k < n) {
+          PairGeom g = load_pair(B, pos, pi, ld_row(row + k));
+          if (g.r2 < T.r_cut_sq) {
+            double rinv = fast_rsqrt(g.r2);
+            double rr = g.r2 * rinv;
+            double x0;
+            int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
+            int hi = max(ti, g.tj), lo = min(ti, g.tj);
+            double mag = spline_fp(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+            double p_ji = spline_fp(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);  // phi(a -> g)
+            double p_ij = p_ji;
+            if (g.tj != ti) p_ij = spline_fp(ld256_nc(T.phi + (size_t)(ti + T.n_types * g.tj) * T.kR + idx), x0);  // phi(g -> a)
+            mag = fma(Fi, p_ji, mag);
+            mag = fma(g.fprime_j, p_ij, mag);
+            double s = mag * rinv;
+            acc.a[j][0] = fma(-s, g.dx, acc.a[j][0]), acc.a[j][1] = fma(-s, g.dy, acc.a[j][1]), acc.a[j][2] = fma(-s, g.dz, acc.a[j][2]);
+          }
+        }
       }
     }
-    gx = group_sum<G>(ax), gy = group_sum<G>(ay), gz = group_sum<G>(az);
+    double tot[3];
+    acc.total(tot);
+    gx = tot[0], gy = tot[1], gz = tot[2];
   }
 
   // F_i'(rho) / F_i(rho) with the OutOfBounds check of Spline::fetch.
@@ -177,20 +244,20 @@ namespace ofly {
       if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
   }
-  template <int G>
-  static __global__ void __launch_bounds__(256) k_eam_force(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
+  // MINB = CTAs per SM the register allocation is capped for (4: 64 registers, a few spilled bytes at G = 4; 3: 80).
+  template <int G, int MINB = 4>
+  static __global__ void __launch_bounds__(256, MINB) k_eam_force(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
                                                             const unsigned long long *__restrict__ offset, size_t offset_stride) {
     eam_force_tiles<G>(B, T, S, out, stride, offset, offset_stride);
   }
 
   // Sub-warp width for `atoms` atoms of work on a chip with `slots` resident threads: few atoms -> wide groups
   // (more threads, shorter per-lane chains: latency), many atoms -> narrow groups (fewer idle lanes on the ragged
-  // row tail: throughput).
-  // Measured on a lone 16 000-atom replica: the widest group that still fits ONE wave of resident threads (the pair
-  // kernels hold ~1024 threads per SM, half of `slots`) is the fastest; a second wave costs more than longer lanes.
+  // row tail: throughput). Measured on a lone 16 000-atom replica: the widest group that still fits ONE wave of
+  // resident threads (the pair kernels hold ~1024 threads per SM, half of `slots`) is the fastest.
+  // The width only decides how the work is spread: the sums are G-invariant (VirtSum), widths are 4, 8 or 16.
   __host__ __device__ inline int group_for(long atoms, long slots) {
     const long wave = slots / 2;
-    if (atoms * 32 <= wave) return 32;
     if (atoms * 16 <= wave) return 16;
     if (atoms * 8 <= wave) return 8;
     return 4;
@@ -198,8 +265,6 @@ namespace ofly {
 
   // The search's tick kernels pick G on the device from the number of replicas still active: for most ticks of
   // a batch only a few replicas are left and the evaluation is a latency chain, not a throughput problem.
-  // (The lane count sets the order of the per-atom sum, so a replica's rounding depends on how many replicas are
-  // active with it: deterministic for a given batch, not identical across batch compositions.)
   // trace (tuning aid, may be null): [0] = count, then (mark, globaltimer) pairs -- block 0 stamps its start and end
   __device__ __forceinline__ void kernel_stamp(unsigned long long *trace, int cap, int mark) {
     if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -215,20 +280,18 @@ namespace ofly {
     switch (group_for((long)(*S.count) * B.N, slots)) {
       case 4: eam_rho_tiles<4>(B, T, S); break;
       case 8: eam_rho_tiles<8>(B, T, S); break;
-      case 16: eam_rho_tiles<16>(B, T, S); break;
-      default: eam_rho_tiles<32>(B, T, S); break;
+      default: eam_rho_tiles<16>(B, T, S); break;
     }
     kernel_stamp(trace, trace_cap, 92);
   }
-  static __global__ void __launch_bounds__(256) k_eam_force_dyn(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
+  static __global__ void __launch_bounds__(256, 4) k_eam_force_dyn(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
                                                                 const unsigned long long *__restrict__ offset, size_t offset_stride, long slots,
                                                                 unsigned long long *trace, int trace_cap) {
     kernel_stamp(trace, trace_cap, 93);
     switch (group_for((long)(*S.count) * B.N, slots)) {
       case 4: eam_force_tiles<4>(B, T, S, out, stride, offset, offset_stride); break;
       case 8: eam_force_tiles<8>(B, T, S, out, stride, offset, offset_stride); break;
-      case 16: eam_force_tiles<16>(B, T, S, out, stride, offset, offset_stride); break;
-      default: eam_force_tiles<32>(B, T, S, out, stride, offset, offset_stride); break;
+      default: eam_force_tiles<16>(B, T, S, out, stride, offset, offset_stride); break;
     }
     kernel_stamp(trace, trace_cap, 94);
   }

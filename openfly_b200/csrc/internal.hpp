@@ -67,6 +67,20 @@ struct ofly_tables {
   std::atomic<int> refs{1};
 };
 
+// The instantiated tick graph of the last search call (search_api.cu): reused while every kernel argument is unchanged.
+struct ofly_search_graph {
+  std::vector<char> key;  // bytes of everything the captured launches depend on
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphConditionalHandle cond_while{}, cond_if{};
+  bool nested = false;
+  void reset() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr, graph = nullptr, key.clear();
+  }
+};
+
 struct ofly_batch {
   ofly_ctx *ctx = nullptr;
   ofly_tables *tables = nullptr;
@@ -89,4 +103,5 @@ struct ofly_batch {
   ofly::DevBuf<int> hess_info;
   std::vector<ofly::DevBuf<char>> io_pool;                   // device staging of the host-pointer search calls
   std::vector<int> fault_host;
+  ofly_search_graph search_graph;
 };

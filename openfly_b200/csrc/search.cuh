@@ -60,12 +60,13 @@ namespace ofly {
     double sy[kMaxHist * kMaxHist], yy[kMaxHist * kMaxHist];
   };
 
-  struct RepState {
+  struct RepState {  // one per resident slot
     int phase, status;
     int iter;     // translation / minimiser step index i
     int rot_it;   // rotor iteration
     int first;    // no step taken yet (first effective gradient / first gradient)
     int need_rebuild;
+    int qid, pad;  // index of the search this slot is running, in the caller's queue of start states
     unsigned long long gdst;  // offset (doubles) inside the replica's workspace for the next gradient
     double trust, acc, convex_count, curv, mag_g;
     double c_x0, b_1, theta_1;  // rotor scalars carried over the trial-gradient request
@@ -78,7 +79,8 @@ namespace ofly {
     int ticket;               // teams that have finished their segment in this tick
     int tick;
     long long kernels;  // kernels executed so far (an IF-guarded rebuild only counts when it ran)
-    int pad[2];
+    int queue_head;     // next search of the queue that no slot has claimed yet
+    int fault_or;       // OR of the fault bits that ended a search (slots are re-armed, their own fault words reset)
   };
 
   struct SearchParams {
@@ -95,11 +97,12 @@ namespace ofly {
     double cos_theta_tol;
     int count_frozen;
     long n_sp;
+    long n_queue;  // searches in the caller's queue (>= 1); the io arrays below are indexed by search, not by slot
     // io (device pointers)
     const double *pos_in, *axis_in, *in_min, *hist_sp;
     double *pos_out, *axis_out, *grad_out;
     int *status;
-    long *counters;  // [R][4] or null
+    long *counters;  // [n_queue][4] or null
     // engine
     double *ws;  // [R][ws_stride] vectors
     size_t ws_stride;
@@ -721,6 +724,8 @@ namespace ofly {
     const SearchParams &P;
     const int r, n3;
     int entry = 0;  // position of this replica in the active list (where its fate is reported)
+    size_t q;       // search of the queue this slot is running
+    bool done = false;  // the search finished in this segment (the slot may take the next one)
     RepState *S;    // global
     Work W;
     // working copies of the persistent scalars
@@ -730,6 +735,7 @@ namespace ofly {
 
     __device__ Segment(Team<C> &tm_, const BatchDev &B_, const SearchParams &P_, int r_) : tm(tm_), B(B_), P(P_), r(r_), n3(3 * B_.N) {
       S = P.state + r;
+      q = (size_t)S->qid;
       const size_t n3p = ((size_t)n3 + 3) & ~(size_t)3;
       double *p = P.ws + (size_t)r * P.ws_stride;
       W.base = p;
@@ -749,7 +755,7 @@ namespace ofly {
       iter = S->iter, rot_it = S->rot_it, first = S->first, need_rebuild = 0;
       trust = S->trust, acc = S->acc, convex_count = S->convex_count, curv = S->curv, mag_g = S->mag_g;
       c_x0 = S->c_x0, b_1 = S->b_1, theta_1 = S->theta_1;
-      for (int q = 0; q < 4; q++) tally[q] = S->tally[q];
+      for (int k = 0; k < 4; k++) tally[k] = S->tally[k];
     }
 
     __device__ double4 *pos() const { return B.pos4 + (size_t)r * B.N; }
@@ -774,27 +780,46 @@ namespace ofly {
         S->c_x0 = c_x0, S->b_1 = b_1, S->theta_1 = theta_1;
         S->trans.k = W.trans.k;
         if (P.mode == 1) S->rot.k = W.rot.k;
-        for (int q = 0; q < 4; q++) S->tally[q] = tally[q];
+        for (int k = 0; k < 4; k++) S->tally[k] = tally[k];
       }
     }
 
-    // Write the results of a finished replica.
+    // Write the results of a finished search.
     __device__ __forceinline__ void finish(int status) {
       __syncthreads();
       for (int t = tm.tid; t < n3; t += tm.nthreads) {
-        P.pos_out[(size_t)r * n3 + t] = W.x[t];
-        if (P.mode == 1) P.axis_out[(size_t)r * n3 + t] = W.axis[t];
-        if (P.mode == 0 && P.grad_out) P.grad_out[(size_t)r * n3 + t] = W.g[t];
+        P.pos_out[q * n3 + t] = W.x[t];
+        if (P.mode == 1) P.axis_out[q * n3 + t] = W.axis[t];
+        if (P.mode == 0 && P.grad_out) P.grad_out[q * n3 + t] = W.g[t];
       }
       if (tm.tid == 0) {
-        P.status[r] = status;
+        P.status[q] = status;
         if (P.counters) {
-          long *c = P.counters + 4 * (size_t)r;
-          for (int q = 0; q < 4; q++) c[q] = tally[q];
+          long *c = P.counters + 4 * q;
+          for (int k = 0; k < 4; k++) c[k] = tally[k];
         }
         S->phase = kDone, S->status = status, S->need_rebuild = 0;
         P.flags[entry] = 0;
+        if (status == kStatusCapacity) atomicOr(&P.ctl->fault_or, kFaultCapacity);
       }
+      done = true;
+    }
+
+    // Continuous refill (saddle::Master::find_n's `while (tot < max_searches)` loop, src/saddle/find.cpp:374-422, without
+    // its batch boundary): a slot whose search has finished claims the next start state of the queue and begins it in
+    // the same segment, so the chip stays full until the queue is empty. Which slot runs which search depends on
+    // timing; what a search computes does not (every sum is independent of the batch composition), and results are
+    // stored by search index. Returns false when the queue is exhausted (the slot then leaves the active list).
+    __device__ __forceinline__ bool take_next_search() {
+      double v[1] = {0.0};
+      if (tm.tid == 0) v[0] = (double)atomicAdd(&P.ctl->queue_head, 1);
+      tm.reduce<1>(v);  // every thread of the team learns the claimed index
+      const long next = (long)v[0];
+      if (next >= P.n_queue) return false;
+      q = (size_t)next;
+      done = false;
+      if (tm.tid == 0) S->qid = (int)next, B.fault[r] = 0;
+      return true;
     }
 
     // neigh::List::rebuild(x) request: the grid kernels of this tick do the work; the histogram of
@@ -833,15 +858,16 @@ namespace ofly {
     }
 
     // ---- minimise::LBFGS::minimise ----------------------------------------------------------------
+    __device__ __forceinline__ void start_minimise() {
+      for (int t = tm.tid; t < n3; t += tm.nthreads) W.x[t] = P.pos_in[q * n3 + t];
+      W.trans.k = 0;
+      iter = 0, first = 1, trust = P.min_trust, acc = 0;
+      for (int k = 0; k < 4; k++) tally[k] = 0;
+      request_rebuild();
+      yield(kMinGrad, W.g);
+    }
     __device__ __forceinline__ void run_minimise(int phase) {
-      if (phase == kInit) {
-        for (int t = tm.tid; t < n3; t += tm.nthreads) W.x[t] = P.pos_in[(size_t)r * n3 + t];
-        W.trans.k = 0;
-        iter = 0, first = 1, trust = P.min_trust, acc = 0;
-        for (int q = 0; q < 4; q++) tally[q] = 0;
-        request_rebuild();
-        return yield(kMinGrad, W.g);
-      }
+      if (phase == kInit) return start_minimise();
       // phase == kMinGrad: the gradient at x is in W.g
       tally[0]++;
       double b2[2] = {0, 0};
@@ -872,22 +898,23 @@ namespace ofly {
 
     // ---- saddle::Rotor::eff_gradient + saddle::Dimer::find_sp ---------------------------------------
     // Returns true if the replica finished or suspended; false never.
+    __device__ __forceinline__ void start_dimer() {
+      for (int t = tm.tid; t < n3; t += tm.nthreads) {
+        W.x[t] = P.pos_in[q * n3 + t];
+        W.axis[t] = P.axis_in[q * n3 + t];
+      }
+      W.trans.k = 0, W.rot.k = 0;
+      iter = 0, rot_it = 0, first = 1, trust = P.min_trust, acc = 0, convex_count = 0;
+      for (int k = 0; k < 4; k++) tally[k] = 0;
+      request_rebuild();
+      yield(kRotG0, W.g0);  // eff_gradient starts with pot.gradient(g0) (rotor.cpp:75)
+    }
     __device__ __forceinline__ void run_dimer(int phase) {
       const double dr = P.delta_r;
       const double inv_n = 1.0 / (double)B.N;
       double *p4 = reinterpret_cast<double *>(pos());
 
-      if (phase == kInit) {
-        for (int t = tm.tid; t < n3; t += tm.nthreads) {
-          W.x[t] = P.pos_in[(size_t)r * n3 + t];
-          W.axis[t] = P.axis_in[(size_t)r * n3 + t];
-        }
-        W.trans.k = 0, W.rot.k = 0;
-        iter = 0, first = 1, trust = P.min_trust, acc = 0, convex_count = 0;
-        for (int q = 0; q < 4; q++) tally[q] = 0;
-        request_rebuild();
-        return yield(kRotG0, W.g0);  // eff_gradient starts with pot.gradient(g0) (rotor.cpp:75)
-      }
+      if (phase == kInit) return start_dimer();
 
       bool rot_head = false, have_torque = false;
       double a7[7] = {0, 0, 0, 0, 0, 0, 0};  // (g1-g0).axis, sum(g1-g0)[3], sum(axis)[3]
@@ -1133,11 +1160,20 @@ namespace ofly {
     const int a = blockIdx.x / C;
     if (a >= n_listed) return;  // whole clusters leave together
     {
-      const int r = P.active[a];
-      const int phase = P.state[r].phase;
+      // One thread reads the slot's header and shares it: the segment overwrites phase / iter before it ends, and a warp
+      // that is late to this point must not see the new values (every CTA of a cluster reads before the cluster barrier
+      // of Team::init, so no peer can be ahead either).
+      __shared__ int head[4];
+      if (threadIdx.x == 0) {
+        const int r0 = P.active[a];
+        head[0] = r0, head[1] = P.state[r0].phase, head[2] = P.state[r0].iter, head[3] = __ldcg(B.fault + r0);
+      }
+      __syncthreads();
+      const int r = head[0];
+      const int phase = head[1];
       if (phase != kDone) {
         tm.init();
-        const int fault = __ldcg(B.fault + r);
+        const int fault = head[3];
         tm.trace_params = &P, tm.trace_r = r;
         tm.mark(1);
         Segment<C> seg(tm, B, P, r);
@@ -1147,7 +1183,7 @@ namespace ofly {
           seg.finish(kStatusCapacity);
         } else if (phase != kInit && (fault & kFaultOutOfBounds)) {
           seg.finish(kStatusOutOfBounds);  // the reference throws Spline::OutOfBounds out of find_sp / minimise
-        } else if (P.state[r].iter < 0) {
+        } else if (head[2] < 0) {
           seg.finish(kStatusUnfinished);
         } else {
           if (phase == kInit && tm.tid == 0) B.fault[r] = 0;
@@ -1155,6 +1191,13 @@ namespace ofly {
             seg.run_minimise(phase);
           } else {
             seg.run_dimer(phase);
+          }
+        }
+        if (seg.done && head[2] >= 0 && seg.take_next_search()) {  // (out of ticks: nothing new is started)
+          if (P.mode == 0) {
+            seg.start_minimise();
+          } else {
+            seg.start_dimer();
           }
         }
         tm.mark(90);
@@ -1209,6 +1252,16 @@ namespace ofly {
         }
       }
     }
+  }
+
+  // Start of a search call: the first n0 = min(slots, queue) searches go to slots 0..n0-1, the queue head stands behind them,
+  // every search is marked unfinished until a slot reports it.
+  static __global__ void k_search_init(SearchParams P, int n0) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nt = gridDim.x * blockDim.x;
+    for (long s = t; s < P.n_queue; s += nt) P.status[s] = kStatusUnfinished;
+    for (int a = t; a < n0; a += nt) P.active[a] = a, P.state[a].qid = a;
+    if (t == 0) P.ctl->n_active = n0, P.ctl->queue_head = n0;
   }
 
 }  // namespace ofly

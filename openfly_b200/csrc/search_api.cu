@@ -54,7 +54,39 @@ namespace ofly {
     // the team is made as wide as the vector allows: >= 2 elements per thread up to a 512-thread CTA, then a
     // cluster while every thread keeps >= 8 elements. The segment kernel strides over the list of active
     // replicas, so wide teams cost extra sweeps only while many replicas are active (the first few % of ticks).
-    TeamShape pick_team(ofly_ctx *, long, long n3) {
+    // Clusters of C 512-thread CTAs of the segment kernel the device can co-schedule (0: the shape cannot launch at
+    // all -- MIG slices, parts with fewer SMs per GPC, ...). Asked once per device and shape.
+    template <int C>
+    int active_clusters(ofly_ctx *ctx) {
+      static std::map<int, int> known;
+      auto it = known.find(ctx->device);
+      if (it != known.end()) return it->second;
+      int n = 0;
+      if (C > 8 && cudaFuncSetAttribute(k_segment<C, kSegMaxThreads>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+      } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(C), cfg.blockDim = dim3(kSegMaxThreads);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, k_segment<C, kSegMaxThreads>, &cfg) != cudaSuccess) cudaGetLastError(), n = 0;
+      }
+      known[ctx->device] = n;
+      return n;
+    }
+    int active_clusters_of(ofly_ctx *ctx, int C) {
+      switch (C) {
+        case 16: return active_clusters<16>(ctx);
+        case 8: return active_clusters<8>(ctx);
+        case 4: return active_clusters<4>(ctx);
+        case 2: return active_clusters<2>(ctx);
+        default: return 1;
+      }
+    }
+
+    TeamShape pick_team(ofly_ctx *ctx, long, long n3) {
       TeamShape t{128, 1};
       while (t.threads < kSegMaxThreads && n3 > (long)t.threads * 2) t.threads *= 2;
       if (t.threads == kSegMaxThreads) {
@@ -66,6 +98,9 @@ namespace ofly {
       if (ft == 128 || ft == 256 || ft == 512) t.threads = ft, t.cluster = 1;
       int forced = env_int("OFLY_CLUSTER", 0);
       if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) t.cluster = forced;
+      // step down while the device cannot co-schedule one cluster of this size (the team width is a property of the
+      // system size and the device, never of the batch, so results stay independent of the batch composition)
+      while (t.cluster > 1 && active_clusters_of(ctx, t.cluster) < 1) t.cluster /= 2;
       return t;
     }
 
@@ -134,8 +169,8 @@ namespace ofly {
     };
     PairGrid pair_grid(ofly_batch *b) {
       int forced = env_int("OFLY_GROUP", 0);
-      if (!(forced == 4 || forced == 8 || forced == 16 || forced == 32)) forced = 0;
-      const int G = forced ? forced : 32;
+      if (!(forced == 4 || forced == 8 || forced == 16)) forced = 0;
+      const int G = forced ? forced : 16;
       const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
       return {forced, stride_grid(b->ctx, tiles, env_int("OFLY_PAIR_CTAS", 32)), (long)b->ctx->sm_count * 2048};
     }
@@ -152,9 +187,6 @@ namespace ofly {
       k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
       const PairGrid pg = pair_grid(b);
       switch (pg.forced) {
-        case 32:
-          k_nb_build<32><<<pg.blocks, 256, 0, st>>>(B, reb);
-          break;
         case 16:
           k_nb_build<16><<<pg.blocks, 256, 0, st>>>(B, reb);
           break;
@@ -180,10 +212,6 @@ namespace ofly {
       const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
       const PairGrid pg = pair_grid(b);
       switch (pg.forced) {
-        case 32:
-          k_eam_rho<32><<<pg.blocks, 256, 0, st>>>(B, T, act);
-          k_eam_force<32><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
-          break;
         case 16:
           k_eam_rho<16><<<pg.blocks, 256, 0, st>>>(B, T, act);
           k_eam_force<16><<<pg.blocks, 256, 0, st>>>(B, T, act, P.ws, P.ws_stride, goff, goff_stride);
@@ -210,15 +238,6 @@ namespace ofly {
       enqueue_gradient(b, P);
     }
 
-    struct GraphGuard {
-      cudaGraph_t graph = nullptr;
-      cudaGraphExec_t exec = nullptr;
-      ~GraphGuard() {
-        if (exec) cudaGraphExecDestroy(exec);
-        if (graph) cudaGraphDestroy(graph);
-      }
-    };
-
     // Ends a capture that an exception interrupted, then rethrows.
     struct CaptureScope {
       cudaStream_t st;
@@ -236,70 +255,89 @@ namespace ofly {
       }
     };
 
+    // Everything a captured tick depends on: the kernels' by-value arguments, the launch shapes and the graph's form.
+    std::vector<char> graph_key(ofly_batch *b, SearchParams const &P, TeamShape shape, bool nested) {
+      const PairGrid pg = pair_grid(b);
+      std::vector<char> k;
+      auto put = [&k](const void *p, size_t n) { k.insert(k.end(), (const char *)p, (const char *)p + n); };
+      put(&P, sizeof P), put(&b->d, sizeof b->d), put(&b->tables->dev, sizeof b->tables->dev);
+      put(&shape, sizeof shape), put(&pg, sizeof pg), put(&nested, sizeof nested);
+      return k;
+    }
+
     // The whole search as ONE graph launch: a WHILE conditional node whose body is one tick; the segment
     // kernel clears the condition when no replica is active. With `nested` the five rebuild kernels sit in
     // an IF node inside the body that the segment kernel arms only when some replica asked for a rebuild
     // (late in a batch most ticks have none, and five empty launches are a sixth of such a tick).
+    // The instantiated graph is kept in the batch and reused while the key above is unchanged (a Master calls with the
+    // same buffers batch after batch); the conditional handles are part of the kernels' arguments, so they are kept too.
     // Returns false if the graph could not be constructed (nothing was launched).
     bool try_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, bool nested) {
       ofly_ctx *ctx = b->ctx;
-      GraphGuard g;
-      try {
-        OFLY_CUDA(cudaGraphCreate(&g.graph, 0));
-        cudaGraphConditionalHandle handle, handle_if{};
-        OFLY_CUDA(cudaGraphConditionalHandleCreate(&handle, g.graph, 1, cudaGraphCondAssignDefault));
-        cudaGraphNodeParams np{};
-        np.type = cudaGraphNodeTypeConditional;
-        np.conditional.handle = handle;
-        np.conditional.type = cudaGraphCondTypeWhile;
-        np.conditional.size = 1;
-        cudaGraphNode_t node;
-        OFLY_CUDA(cudaGraphAddNode(&node, g.graph, nullptr, 0, &np));
-        cudaGraph_t body = np.conditional.phGraph_out[0];
-        P.use_cond = 1, P.cond = handle;
-        cudaGraph_t if_body = nullptr;
-        if (nested) {
-          OFLY_CUDA(cudaGraphConditionalHandleCreate(&handle_if, g.graph, 0, cudaGraphCondAssignDefault));
-          P.use_cond_rebuild = 1, P.cond_rebuild = handle_if;
-        }
-        {
-          OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-          CaptureScope cap(ctx->stream);
-          enqueue_segment(b, P, shape);
+      ofly_search_graph &g = b->search_graph;
+      P.use_cond = 0, P.use_cond_rebuild = 0, P.cond = cudaGraphConditionalHandle{}, P.cond_rebuild = cudaGraphConditionalHandle{};
+      std::vector<char> key = graph_key(b, P, shape, nested);
+      const bool reuse = g.exec != nullptr && g.key == key && !std::getenv("OFLY_NO_GRAPH_CACHE");
+      if (!reuse) {
+        g.reset();
+        try {
+          OFLY_CUDA(cudaGraphCreate(&g.graph, 0));
+          OFLY_CUDA(cudaGraphConditionalHandleCreate(&g.cond_while, g.graph, 1, cudaGraphCondAssignDefault));
+          cudaGraphNodeParams np{};
+          np.type = cudaGraphNodeTypeConditional;
+          np.conditional.handle = g.cond_while;
+          np.conditional.type = cudaGraphCondTypeWhile;
+          np.conditional.size = 1;
+          cudaGraphNode_t node;
+          OFLY_CUDA(cudaGraphAddNode(&node, g.graph, nullptr, 0, &np));
+          cudaGraph_t body = np.conditional.phGraph_out[0];
+          P.use_cond = 1, P.cond = g.cond_while;
+          cudaGraph_t if_body = nullptr;
           if (nested) {
-            cudaStreamCaptureStatus status;
-            const cudaGraphNode_t *deps = nullptr;
-            size_t n_deps = 0;
-            OFLY_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, nullptr, &deps, &n_deps));
-            cudaGraphNodeParams ip{};
-            ip.type = cudaGraphNodeTypeConditional;
-            ip.conditional.handle = handle_if;
-            ip.conditional.type = cudaGraphCondTypeIf;
-            ip.conditional.size = 1;
-            cudaGraphNode_t if_node;
-            OFLY_CUDA(cudaGraphAddNode(&if_node, body, deps, n_deps, &ip));
-            if_body = ip.conditional.phGraph_out[0];
-            OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
-          } else {
-            enqueue_rebuild(b, P);
+            OFLY_CUDA(cudaGraphConditionalHandleCreate(&g.cond_if, g.graph, 0, cudaGraphCondAssignDefault));
+            P.use_cond_rebuild = 1, P.cond_rebuild = g.cond_if;
           }
-          enqueue_gradient(b, P);
-          cap.end();
+          {
+            OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            CaptureScope cap(ctx->stream);
+            enqueue_segment(b, P, shape);
+            if (nested) {
+              cudaStreamCaptureStatus status;
+              const cudaGraphNode_t *deps = nullptr;
+              size_t n_deps = 0;
+              OFLY_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, nullptr, &deps, &n_deps));
+              cudaGraphNodeParams ip{};
+              ip.type = cudaGraphNodeTypeConditional;
+              ip.conditional.handle = g.cond_if;
+              ip.conditional.type = cudaGraphCondTypeIf;
+              ip.conditional.size = 1;
+              cudaGraphNode_t if_node;
+              OFLY_CUDA(cudaGraphAddNode(&if_node, body, deps, n_deps, &ip));
+              if_body = ip.conditional.phGraph_out[0];
+              OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
+            } else {
+              enqueue_rebuild(b, P);
+            }
+            enqueue_gradient(b, P);
+            cap.end();
+          }
+          if (nested) {
+            OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, if_body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            CaptureScope cap(ctx->stream);
+            enqueue_rebuild(b, P);
+            cap.end();
+          }
+          OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+          g.key = std::move(key), g.nested = nested;
+        } catch (Error const &e) {
+          cudaGetLastError();
+          g.reset();
+          if (!nested) throw;
+          if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: nested rebuild IF node unavailable (%s); flat tick graph\n", e.what());
+          return false;
         }
-        if (nested) {
-          OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, if_body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-          CaptureScope cap(ctx->stream);
-          enqueue_rebuild(b, P);
-          cap.end();
-        }
-        OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
-      } catch (Error const &e) {
-        cudaGetLastError();
-        if (!nested) throw;
-        if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: nested rebuild IF node unavailable (%s); flat tick graph\n", e.what());
-        return false;
+        if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: search graph with %s rebuild\n", nested ? "IF-guarded" : "unconditional");
       }
-      if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: search graph with %s rebuild\n", nested ? "IF-guarded" : "unconditional");
       OFLY_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
       OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
       return true;
@@ -334,12 +372,15 @@ namespace ofly {
     };
 
     // Shared driver: grid set-up, workspace, launch, capacity-fault retry. All pointers are device memory.
-    void run_search(ofly_batch *b, SearchParams P, double base_radius, double skin_frac, DevPtrs io) {
+    // `n_queue` searches run through the batch's R resident slots (n_queue == R: the reference's batch call).
+    void run_search(ofly_batch *b, SearchParams P, double base_radius, double skin_frac, DevPtrs io, long n_queue) {
       ofly_ctx *ctx = b->ctx;
       OFLY_CUDA(cudaSetDevice(ctx->device));
       require(P.n_hist >= 1 && P.n_hist <= kMaxHist, "L-BFGS history size must be in [1, 16]");
       require(P.mode == 0 || (P.rot_n >= 1 && P.rot_n <= kMaxHist), "rotor L-BFGS history size must be in [1, 16]");
       require(P.iter_max >= 0, "iteration limit is negative");
+      require(n_queue >= 1 && n_queue < (1L << 30), "number of searches must be in [1, 2^30)");
+      P.n_queue = n_queue;
 
       // skin = max(skin_frac^(1/3) - 1, 0) * r   (lbfgs.cpp:39, dimer.cpp:47)
       double skin = std::max(std::pow(skin_frac, 1. / 3.) - 1, 0.0) * base_radius;
@@ -368,7 +409,9 @@ namespace ofly {
       // gradient requests per replica are bounded by steps x (2 + rotations); the budget only guards
       // against a device-side loop that would otherwise never end.
       const long per_step = P.mode == 0 ? 1 : 2 + 10L * std::max(1, P.iter_max_rot) + 2;
-      P.max_ticks = (int)std::min<long>((long)(P.iter_max + 1) * per_step + 8, 1L << 30);
+      const long n0 = std::min<long>(b->R, n_queue);
+      const long rounds = (n_queue + n0 - 1) / n0;  // searches a slot may run one after the other
+      P.max_ticks = (int)std::min<long>(((long)(P.iter_max + 1) * per_step + 8) * rounds, 1L << 30);
 
       // OFLY_LBFGS=twoloop selects the pass-per-pair recursion (A/B comparisons); default is the single-pass step.
       P.gram = [] {
@@ -414,9 +457,9 @@ namespace ofly {
 
       for (int attempt = 0;; attempt++) {
         OFLY_CUDA(cudaMemsetAsync(base, 0, head, ctx->stream));
-        // tick 0: every replica is active (sel_all = 0..R-1 followed by R)
-        OFLY_CUDA(cudaMemcpyAsync(P.active, b->sel_all.p, R * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-        OFLY_CUDA(cudaMemcpyAsync(&P.ctl->n_active, b->sel_all.p + R, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        // tick 0: the first n0 searches of the queue are active, one per slot
+        k_search_init<<<(unsigned)std::min<long>((n_queue + 255) / 256, 1024), 256, 0, ctx->stream>>>(P, (int)n0);
+        OFLY_CUDA(cudaGetLastError());
         if (device_loop) {
           run_device_loop(b, P, shape);
         } else {
@@ -430,6 +473,7 @@ namespace ofly {
         ctx->launches += (long)c.kernels;  // kernels executed (by the device-side loop or the host loop)
         ctx->ticks += c.tick;
         if (c.n_active != 0) throw Error(OFLY_ERR_CUDA, "search loop ended with active replicas");
+        f |= c.fault_or;
         if (!(f & kFaultCapacity)) break;
         if (attempt == 2) throw Error(OFLY_ERR_CAPACITY, "neighbour buffers overflowed after regrowing");
         grow_buffers(b);
@@ -503,60 +547,73 @@ void ofly_rotor_options_default(ofly_rotor_options *o) {
   o->n = 6, o->iter_max_rot = 20, o->relax_in_convex = 1, o->delta_r = 0.001, o->theta_tol = 1 * M_PI / 360.;
 }
 
-int ofly_lbfgs_minimise_dev(ofly_batch *b, const ofly_lbfgs_options *opt, const double *pos_in_dev, double *pos_out_dev,
-                            double *grad_out_dev, int *status_dev, long *counters_dev) {
+int ofly_lbfgs_minimise_stream_dev(ofly_batch *b, const ofly_lbfgs_options *opt, long n_searches, const double *pos_in_dev, double *pos_out_dev,
+                                   double *grad_out_dev, int *status_dev, long *counters_dev) {
   return guarded([&] {
     require(b && opt && pos_in_dev && pos_out_dev && status_dev, "null argument");
     DevPtrs io{pos_in_dev, nullptr, nullptr, nullptr, pos_out_dev, nullptr, grad_out_dev, status_dev, counters_dev};
-    run_search(b, lbfgs_params(*opt), b->tables->host.r_cut, opt->skin_frac, io);
+    run_search(b, lbfgs_params(*opt), b->tables->host.r_cut, opt->skin_frac, io, n_searches);
   });
 }
 
-int ofly_lbfgs_minimise(ofly_batch *b, const ofly_lbfgs_options *opt, const double *pos_in_host, double *pos_out_host,
-                        double *grad_out_host, int *status_host, long *counters_host) {
+int ofly_lbfgs_minimise_stream(ofly_batch *b, const ofly_lbfgs_options *opt, long n_searches, const double *pos_in_host, double *pos_out_host,
+                               double *grad_out_host, int *status_host, long *counters_host) {
   return guarded([&] {
     require(b && opt && pos_in_host && pos_out_host && status_host, "null argument");
+    require(n_searches >= 1, "number of searches must be positive");
     OFLY_CUDA(cudaSetDevice(b->ctx->device));
-    size_t nv = (size_t)b->R * 3 * (size_t)b->N, R = (size_t)b->R;
+    size_t nv = (size_t)n_searches * 3 * (size_t)b->N, Q = (size_t)n_searches;
     Arena A(b);
     DevPtrs io{};
     io.pos_in = A.upload(pos_in_host, nv);
     io.pos_out = A.alloc<double>(nv);
     io.grad_out = A.alloc<double>(nv);
-    io.status = A.alloc<int>(R);
-    io.counters = A.alloc<long>(4 * R);
-    run_search(b, lbfgs_params(*opt), b->tables->host.r_cut, opt->skin_frac, io);
+    io.status = A.alloc<int>(Q);
+    io.counters = A.alloc<long>(4 * Q);
+    run_search(b, lbfgs_params(*opt), b->tables->host.r_cut, opt->skin_frac, io, n_searches);
     cudaStream_t st = b->ctx->stream;
     OFLY_CUDA(cudaMemcpyAsync(pos_out_host, io.pos_out, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (grad_out_host) OFLY_CUDA(cudaMemcpyAsync(grad_out_host, io.grad_out, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-    OFLY_CUDA(cudaMemcpyAsync(status_host, io.status, R * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (counters_host) OFLY_CUDA(cudaMemcpyAsync(counters_host, io.counters, 4 * R * sizeof(long), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaMemcpyAsync(status_host, io.status, Q * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (counters_host) OFLY_CUDA(cudaMemcpyAsync(counters_host, io.counters, 4 * Q * sizeof(long), cudaMemcpyDeviceToHost, st));
     OFLY_CUDA(cudaStreamSynchronize(st));
   });
 }
 
-int ofly_dimer_find_sp_dev(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, const double *pos_in_dev,
-                           const double *axis_in_dev, const double *in_min_dev, const double *hist_sp_dev, long n_hist,
-                           double theta_tol, int count_frozen, double *pos_out_dev, double *axis_out_dev, int *exit_code_dev,
-                           long *counters_dev) {
+int ofly_lbfgs_minimise_dev(ofly_batch *b, const ofly_lbfgs_options *opt, const double *pos_in_dev, double *pos_out_dev,
+                            double *grad_out_dev, int *status_dev, long *counters_dev) {
+  return ofly_lbfgs_minimise_stream_dev(b, opt, b ? b->R : 0, pos_in_dev, pos_out_dev, grad_out_dev, status_dev, counters_dev);
+}
+
+int ofly_lbfgs_minimise(ofly_batch *b, const ofly_lbfgs_options *opt, const double *pos_in_host, double *pos_out_host,
+                        double *grad_out_host, int *status_host, long *counters_host) {
+  return ofly_lbfgs_minimise_stream(b, opt, b ? b->R : 0, pos_in_host, pos_out_host, grad_out_host, status_host, counters_host);
+}
+
+int ofly_dimer_find_sp_stream_dev(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, long n_searches,
+                                  const double *pos_in_dev, const double *axis_in_dev, const double *in_min_dev, const double *hist_sp_dev,
+                                  long n_hist, double theta_tol, int count_frozen, double *pos_out_dev, double *axis_out_dev,
+                                  int *exit_code_dev, long *counters_dev) {
   return guarded([&] {
     require(b && opt && ropt && pos_in_dev && axis_in_dev && pos_out_dev && axis_out_dev && exit_code_dev, "null argument");
     require(n_hist == 0 || (in_min_dev && hist_sp_dev), "history given without in_min / hist_sp");
     DevPtrs io{pos_in_dev, axis_in_dev, in_min_dev, hist_sp_dev, pos_out_dev, axis_out_dev, nullptr, exit_code_dev, counters_dev};
     // list radius: rotor.r_cut(pot) = pot.r_cut + 2 delta_r (rotor.hpp:123) plus the skin (dimer.cpp:47-53)
-    run_search(b, dimer_params(*opt, *ropt, theta_tol, count_frozen, n_hist), b->tables->host.r_cut + 2 * ropt->delta_r, opt->skin_frac, io);
+    run_search(b, dimer_params(*opt, *ropt, theta_tol, count_frozen, n_hist), b->tables->host.r_cut + 2 * ropt->delta_r, opt->skin_frac, io,
+               n_searches);
   });
 }
 
-int ofly_dimer_find_sp(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, const double *pos_in_host,
-                       const double *axis_in_host, const double *in_min_host, const double *hist_sp_host, long n_hist,
-                       double theta_tol, int count_frozen, double *pos_out_host, double *axis_out_host, int *exit_code_host,
-                       long *counters_host) {
+int ofly_dimer_find_sp_stream(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, long n_searches,
+                              const double *pos_in_host, const double *axis_in_host, const double *in_min_host, const double *hist_sp_host,
+                              long n_hist, double theta_tol, int count_frozen, double *pos_out_host, double *axis_out_host,
+                              int *exit_code_host, long *counters_host) {
   return guarded([&] {
     require(b && opt && ropt && pos_in_host && axis_in_host && pos_out_host && axis_out_host && exit_code_host, "null argument");
     require(n_hist == 0 || (in_min_host && hist_sp_host), "history given without in_min / hist_sp");
+    require(n_searches >= 1, "number of searches must be positive");
     OFLY_CUDA(cudaSetDevice(b->ctx->device));
-    size_t n3 = 3 * (size_t)b->N, nv = (size_t)b->R * n3, R = (size_t)b->R;
+    size_t n3 = 3 * (size_t)b->N, nv = (size_t)n_searches * n3, Q = (size_t)n_searches;
     Arena A(b);
     DevPtrs io{};
     io.pos_in = A.upload(pos_in_host, nv);
@@ -565,16 +622,33 @@ int ofly_dimer_find_sp(ofly_batch *b, const ofly_dimer_options *opt, const ofly_
     io.hist_sp = n_hist ? A.upload(hist_sp_host, (size_t)n_hist * n3) : nullptr;
     io.pos_out = A.alloc<double>(nv);
     io.axis_out = A.alloc<double>(nv);
-    io.status = A.alloc<int>(R);
-    io.counters = A.alloc<long>(4 * R);
-    run_search(b, dimer_params(*opt, *ropt, theta_tol, count_frozen, n_hist), b->tables->host.r_cut + 2 * ropt->delta_r, opt->skin_frac, io);
+    io.status = A.alloc<int>(Q);
+    io.counters = A.alloc<long>(4 * Q);
+    run_search(b, dimer_params(*opt, *ropt, theta_tol, count_frozen, n_hist), b->tables->host.r_cut + 2 * ropt->delta_r, opt->skin_frac, io,
+               n_searches);
     cudaStream_t st = b->ctx->stream;
     OFLY_CUDA(cudaMemcpyAsync(pos_out_host, io.pos_out, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     OFLY_CUDA(cudaMemcpyAsync(axis_out_host, io.axis_out, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-    OFLY_CUDA(cudaMemcpyAsync(exit_code_host, io.status, R * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (counters_host) OFLY_CUDA(cudaMemcpyAsync(counters_host, io.counters, 4 * R * sizeof(long), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaMemcpyAsync(exit_code_host, io.status, Q * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (counters_host) OFLY_CUDA(cudaMemcpyAsync(counters_host, io.counters, 4 * Q * sizeof(long), cudaMemcpyDeviceToHost, st));
     OFLY_CUDA(cudaStreamSynchronize(st));
   });
+}
+
+int ofly_dimer_find_sp_dev(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, const double *pos_in_dev,
+                           const double *axis_in_dev, const double *in_min_dev, const double *hist_sp_dev, long n_hist,
+                           double theta_tol, int count_frozen, double *pos_out_dev, double *axis_out_dev, int *exit_code_dev,
+                           long *counters_dev) {
+  return ofly_dimer_find_sp_stream_dev(b, opt, ropt, b ? b->R : 0, pos_in_dev, axis_in_dev, in_min_dev, hist_sp_dev, n_hist, theta_tol,
+                                       count_frozen, pos_out_dev, axis_out_dev, exit_code_dev, counters_dev);
+}
+
+int ofly_dimer_find_sp(ofly_batch *b, const ofly_dimer_options *opt, const ofly_rotor_options *ropt, const double *pos_in_host,
+                       const double *axis_in_host, const double *in_min_host, const double *hist_sp_host, long n_hist,
+                       double theta_tol, int count_frozen, double *pos_out_host, double *axis_out_host, int *exit_code_host,
+                       long *counters_host) {
+  return ofly_dimer_find_sp_stream(b, opt, ropt, b ? b->R : 0, pos_in_host, axis_in_host, in_min_host, hist_sp_host, n_hist, theta_tol,
+                                   count_frozen, pos_out_host, axis_out_host, exit_code_host, counters_host);
 }
 
 }  // extern "C"

@@ -39,12 +39,8 @@ namespace ofly {
   namespace {
 
     struct Reader {
-      std::ifstream in;
-      explicit Reader(std::string const &path) : in(path) {
-        if (!in.good()) {
-          throw std::runtime_error("Could not open eam file '" + path + "'");
-        }
-      }
+      std::istream &in;
+      explicit Reader(std::istream &stream) : in(stream) {}
       std::istringstream line() {
         std::string s;
         if (!std::getline(in, s)) {
@@ -76,7 +72,15 @@ namespace ofly {
   }  // namespace
 
   HostTables read_setfl(std::string const &path) {
-    Reader rd(path);
+    std::ifstream in(path);
+    if (!in.good()) {
+      throw std::runtime_error("Could not open eam file '" + path + "'");
+    }
+    return read_setfl(in);
+  }
+
+  HostTables read_setfl(std::istream &in) {
+    Reader rd(in);
     HostTables t;
 
     for (int i = 0; i < 3; ++i) {

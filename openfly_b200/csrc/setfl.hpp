@@ -6,6 +6,7 @@
 // Compiled with -ffp-contract=off so no FMA changes the coefficient bits.
 #pragma once
 
+#include <istream>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,8 @@ namespace ofly {
 
   // Throws std::runtime_error on malformed input.
   HostTables read_setfl(std::string const &path);
+  // DataEAM(std::istream) (data.cpp:67): the same parse from any stream.
+  HostTables read_setfl(std::istream &in);
 
   // Coefficients of the natural cubic spline through `y` (uniform spacing dx), y.size()+4 knots.
   std::vector<Knot> natural_spline(std::vector<double> y, double dx);

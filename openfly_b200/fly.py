@@ -90,10 +90,17 @@ class Box:
 class DataEAM:
     """Parsed + splined setfl tables resident on the device (shared, immutable, ref-counted)."""
 
-    def __init__(self, ctx: Context, path: str):
+    def __init__(self, ctx: Context, path: str | None = None, *, text: bytes | None = None, _handle=None):
+        """DataEAM(path) reads a setfl file; DataEAM(text=...) parses the same from memory (the reference's
+        std::istream constructor, data.cpp:67); from_knots() takes already-splined tables."""
         self.ctx = ctx
         h = C.c_void_p()
-        check(ctx.lib.ofly_tables_load_setfl(ctx.h, path.encode(), C.byref(h)))
+        if _handle is not None:
+            h = _handle
+        elif text is not None:
+            check(ctx.lib.ofly_tables_load_setfl_mem(ctx.h, text, len(text), C.byref(h)))
+        else:
+            check(ctx.lib.ofly_tables_load_setfl(ctx.h, path.encode(), C.byref(h)))
         self.h = h
         info = np.zeros(3, dtype=np.int64)
         dinfo = np.zeros(3 + 8, dtype=np.float64)
@@ -101,6 +108,24 @@ class DataEAM:
         self.n_types, self.knots_rho, self.knots_r = (int(x) for x in info)
         self.d_rho, self.d_r, self._rcut = (float(x) for x in dinfo[:3])
         self.mass = dinfo[3:3 + self.n_types].copy()
+        self.names = [ctx.lib.ofly_tables_type_name(self.h, i).decode() for i in range(self.n_types)]
+
+    @classmethod
+    def from_knots(cls, ctx: Context, names, mass, d_rho: float, d_r: float, r_cut: float, F, phi, V) -> "DataEAM":
+        """F: [n, kF, 4], phi: [n*n, kR, 4] (slot src + n*dst), V: [n*n, kR, 4] (slot max + n*min) spline knots {a,b,c,d}."""
+        F, phi, V = f64(F), f64(phi), f64(V)
+        n = len(names)
+        arr = (C.c_char_p * n)(*[x.encode() for x in names])
+        m = f64(mass)
+        h = C.c_void_p()
+        check(ctx.lib.ofly_tables_create_from_knots(ctx.h, n, arr, ptr(m, _dp), F.shape[1], d_rho, phi.shape[1], d_r, r_cut,
+                                                    ptr(F, _dp), ptr(phi, _dp), ptr(V, _dp), C.byref(h)))
+        return cls(ctx, _handle=h)
+
+    def check_type_map(self, names) -> None:
+        """EAM's constructor check (eam.hpp:50-63): raises unless `names` starts with the table's type names."""
+        arr = (C.c_char_p * len(names))(*[x.encode() for x in names])
+        check(self.ctx.lib.ofly_eam_check_type_map(self.h, len(names), arr))
 
     def rcut(self) -> float:
         return self._rcut
@@ -138,6 +163,13 @@ class System:
         if a.size != self.R * self.N * 3:
             raise OflyError(capi.OFLY_ERR_INVALID, f"expected {self.R}x{self.N}x3 values, got {a.size}")
         return a.reshape(self.R, self.N, 3)
+
+    def _queue(self, a) -> np.ndarray:
+        """[Q, N, 3] start states of a queue of searches (any Q >= 1) that run through this system's R slots."""
+        a = f64(a)
+        if a.size == 0 or a.size % (self.N * 3):
+            raise OflyError(capi.OFLY_ERR_INVALID, f"expected Qx{self.N}x3 values, got {a.size}")
+        return a.reshape(-1, self.N, 3)
 
     def close(self) -> None:
         if self.h:
@@ -211,8 +243,12 @@ class List:
 class Generic:
     """potential::Generic holding an EAM: r_cut / energy / gradient / hessian over a List."""
 
-    def __init__(self, data: DataEAM):
+    def __init__(self, data: DataEAM, type_map=None):
+        """type_map: the caller's type names by id (system::TypeMap); checked against the table as EAM's constructor
+        does (eam.hpp:50-63) when given."""
         self.data = data
+        if type_map is not None:
+            data.check_type_map(list(type_map))
 
     def r_cut(self) -> float:
         return self.data.rcut()
@@ -276,13 +312,15 @@ class LBFGS:
         self.status = None
 
     def minimise(self, system: System, positions, pot: Generic, num_threads: int = 1, raise_oob: bool = True):
-        p = system._vec(positions)
+        """positions: [Q, N, 3]; Q == system.R is the reference's batch, any other Q streams through the R slots."""
+        p = system._queue(positions)
+        Q = p.shape[0]
         out_r = np.zeros_like(p)
         out_g = np.zeros_like(p)
-        status = np.zeros(system.R, dtype=np.int32)
-        cnt = np.zeros((system.R, 4), dtype=np.int64)
-        check(system.ctx.lib.ofly_lbfgs_minimise(system.h, C.byref(self.opt), ptr(p, _dp), ptr(out_r, _dp), ptr(out_g, _dp),
-                                                 ptr(status, _ip), ptr(cnt, _lp)))
+        status = np.zeros(Q, dtype=np.int32)
+        cnt = np.zeros((Q, 4), dtype=np.int64)
+        check(system.ctx.lib.ofly_lbfgs_minimise_stream(system.h, C.byref(self.opt), Q, ptr(p, _dp), ptr(out_r, _dp), ptr(out_g, _dp),
+                                                        ptr(status, _ip), ptr(cnt, _lp)))
         self.status = status
         if raise_oob and (status == -5).any():
             raise OutOfBounds(capi.OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region")
@@ -290,8 +328,10 @@ class LBFGS:
 
 
 class Dimer:
-    """saddle::Dimer(opt, rotor opt, box). find_sp() returns (positions, axis, exit[R], counters[R,4]) with
-    exit codes Dimer::Exit (0 success, -1 convex, -2 iter_max, -3 collision); -5 marks OutOfBounds."""
+    """saddle::Dimer(opt, rotor opt, box). find_sp() returns (positions, axis, exit[Q], counters[Q,4]) with
+    exit codes Dimer::Exit (0 success, -1 convex, -2 iter_max, -3 collision); -5 marks OutOfBounds. positions / axis
+    are [Q, N, 3]: Q == system.R is the reference's batch; any other Q is a queue that streams through the R slots
+    (a finished slot takes the next start state on the device), with the same per-search results."""
 
     success, convex, iter_max, collision, uninit = 0, -1, -2, -3, -4
 
@@ -301,17 +341,20 @@ class Dimer:
 
     def find_sp(self, system: System, positions, axis, in_min, pot: Generic, hist_sp=None, theta_tol: float = np.pi / 6,
                 count_frozen: int = 0, num_threads: int = 1, raise_oob: bool = False):
-        p = system._vec(positions)
-        ax = system._vec(axis)
+        p = system._queue(positions)
+        ax = system._queue(axis)
+        Q = p.shape[0]
+        if ax.shape != p.shape:
+            raise OflyError(capi.OFLY_ERR_INVALID, "positions and axes differ in shape")
         mn = f64(in_min).reshape(system.N, 3)
         hist = f64(np.zeros((0, system.N, 3)) if hist_sp is None else hist_sp).reshape(-1, system.N, 3)
         out_r = np.zeros_like(p)
         out_ax = np.zeros_like(p)
-        code = np.zeros(system.R, dtype=np.int32)
-        cnt = np.zeros((system.R, 4), dtype=np.int64)
-        check(system.ctx.lib.ofly_dimer_find_sp(system.h, C.byref(self.opt), C.byref(self.r_opt), ptr(p, _dp), ptr(ax, _dp),
-                                                ptr(mn, _dp), ptr(hist, _dp), hist.shape[0], theta_tol, count_frozen,
-                                                ptr(out_r, _dp), ptr(out_ax, _dp), ptr(code, _ip), ptr(cnt, _lp)))
+        code = np.zeros(Q, dtype=np.int32)
+        cnt = np.zeros((Q, 4), dtype=np.int64)
+        check(system.ctx.lib.ofly_dimer_find_sp_stream(system.h, C.byref(self.opt), C.byref(self.r_opt), Q, ptr(p, _dp), ptr(ax, _dp),
+                                                       ptr(mn, _dp), ptr(hist, _dp), hist.shape[0], theta_tol, count_frozen,
+                                                       ptr(out_r, _dp), ptr(out_ax, _dp), ptr(code, _ip), ptr(cnt, _lp)))
         if raise_oob and (code == -5).any():
             raise OutOfBounds(capi.OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region")
         return out_r, out_ax, code, cnt

@@ -195,3 +195,99 @@ def test_hessian_eigenvalues_on_device(gpu, otab, oracle_lib):
     Hm = osys.hessian(ids, np.zeros(len(ids), np.uint8), 8, mass_weight=True)
     assert np.abs(evm - fly.hessian_eigenvalues(Hm)).max() < 1e-10
     s.close()
+
+
+def test_sums_do_not_depend_on_subwarp_width(gpu):
+    """Every per-atom sum is defined over 16 virtual lanes (eam.cuh, VirtSum): 4, 8 or 16 physical lanes per atom give
+    the same bits, so energies / forces do not depend on the batch size (which picks the width)."""
+    import os
+
+    fly, ctx, data = gpu
+    pos, ex, ids = bcc_vacancy(6, a=2.855, remove=(1,), jitter=0.05, hydrogen=True)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, replicas=3)
+    nl = fly.List(s, data.rcut() + 0.17)
+    nl.rebuild(np.stack([pos, pos + 0.01, pos - 0.02]))
+    pot = fly.Generic(data)
+    got = {}
+    try:
+        for G in (4, 8, 16):
+            os.environ["OFLY_GROUP"] = str(G)
+            got[G] = (pot.energy(nl), pot.gradient(nl))
+    finally:
+        del os.environ["OFLY_GROUP"]
+    for G in (8, 16):
+        assert np.array_equal(got[G][0], got[4][0]) and np.array_equal(got[G][1], got[4][1])
+    s.close()
+    # and a replica alone gives the bits it gives inside a batch of 3 (other width, other grid)
+    s1 = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl1 = fly.List(s1, data.rcut() + 0.17)
+    nl1.rebuild(pos + 0.01)
+    assert np.array_equal(pot.gradient(nl1)[0], got[4][1][1]) and pot.energy(nl1)[0] == got[4][0][1]
+    s1.close()
+
+
+def test_tables_from_memory_and_from_knots(gpu):
+    """DataEAM(std::istream) (data.cpp:67) and tables handed over as knots: same bits as the path constructor; EAM's
+    TypeMap check (eam.hpp:50-63)."""
+    fly, ctx, data = gpu
+    mem = fly.DataEAM(ctx, text=open(WEN, "rb").read())
+    sel = [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1), (2, 0, 0), (2, 1, 0), (2, 1, 1)]
+    for kind, i, j in sel:
+        assert np.array_equal(mem.knots(kind, i, j), data.knots(kind, i, j))
+    assert mem.names == ["Fe", "H"] and mem.rcut() == data.rcut()
+    n = data.n_types
+    F = np.stack([data.knots(0, i) for i in range(n)])
+    phi = np.zeros((n * n, data.knots_r, 4))
+    V = np.zeros((n * n, data.knots_r, 4))
+    for i in range(n):
+        for j in range(n):
+            phi[i + n * j] = data.knots(1, i, j)
+            V[max(i, j) + n * min(i, j)] = data.knots(2, i, j)
+    kn = fly.DataEAM.from_knots(ctx, data.names, data.mass, data.d_rho, data.d_r, data.rcut(), F, phi, V)
+    pos, ex, ids = bcc_vacancy(4, jitter=0.03, hydrogen=True)
+    out = []
+    for d in (data, mem, kn):
+        s = fly.System(d, fly.Box(tuple(ex)), ids)
+        nl = fly.List(s, d.rcut())
+        nl.rebuild(pos)
+        pot = fly.Generic(d, type_map=["Fe", "H"])
+        out.append((pot.energy(nl), pot.gradient(nl)))
+        s.close()
+    for e, g in out[1:]:
+        assert np.array_equal(e, out[0][0]) and np.array_equal(g, out[0][1])
+    with pytest.raises(fly.OflyError, match="Not enough types"):
+        fly.Generic(data, type_map=["Fe"])
+    with pytest.raises(fly.OflyError, match="TypeID mismatch"):
+        fly.Generic(data, type_map=["H", "Fe"])
+    fly.Generic(data, type_map=["Fe", "H", "He"])  # more types than the table is fine
+    mem.close(), kn.close()
+
+
+def test_out_of_table_negative_density(gpu):
+    """Spline::fetch converts x / dx with static_cast<size_t> (spline.hpp:135-143): an argument <= -dx (a negative embedding
+    density from a table whose phi goes negative) is an OutOfBounds in the reference, never a read before the table."""
+    fly, ctx, data = gpu
+    n = data.n_types
+    F = np.stack([data.knots(0, i) for i in range(n)])
+    phi = np.zeros((n * n, data.knots_r, 4))
+    V = np.zeros((n * n, data.knots_r, 4))
+    for i in range(n):
+        for j in range(n):
+            phi[i + n * j] = -data.knots(1, i, j)  # every density contribution negated
+            V[max(i, j) + n * min(i, j)] = data.knots(2, i, j)
+    neg = fly.DataEAM.from_knots(ctx, data.names, data.mass, data.d_rho, data.d_r, data.rcut(), F, phi, V)
+    pos, ex, ids = bcc_vacancy(4, hydrogen=False)
+    s = fly.System(neg, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, neg.rcut())
+    nl.rebuild(pos)
+    pot = fly.Generic(neg)
+    with pytest.raises(fly.OutOfBounds):
+        pot.gradient(nl)
+    with pytest.raises(fly.OutOfBounds):
+        pot.energy(nl)
+    s.close()
+    s = fly.System(data, fly.Box(tuple(ex)), ids)  # the context survived
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(pos)
+    assert np.isfinite(fly.Generic(data).energy(nl)[0])
+    s.close(), neg.close()

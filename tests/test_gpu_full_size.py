@@ -137,3 +137,55 @@ def test_c5_sized_search_batch_properties(gpu):
     again = fly.Dimer().find_sp(sR, P, A, rmin[0], pot)
     assert np.array_equal(again[2], code) and np.array_equal(again[0], out_r) and np.array_equal(again[3], cnt)
     sR.close()
+
+
+def test_c2_searches_against_oracle_at_benchmark_size(gpu, oracle_lib, capsys):
+    """Search-level parity at the benchmarked size (BASELINE configs[1]): the bench's own 64 start states on the 16 000-atom
+    cell run as one batch on the GPU; 8 of them are re-run to completion by the CPU oracle (one single-threaded search per
+    core, as saddle::Master) and compared: exit codes equal, saddles to 1e-5 A, barriers to 1e-6 eV (src/saddle/dimer.cpp:28-171).
+    The 8 are the searches with the most gradient evaluations among those that end within 500 evaluations on the GPU, both
+    exit kinds included -- the cap only bounds the CPU time of the check (the longest C2 searches take the oracle minutes)."""
+    from openfly_b200 import inputs
+
+    fly, ctx, data = gpu
+    pos, ex, ids = inputs.iron_hydrogen_cell(20, 2.8553, remove=(1,), hydrogen=True)
+    N = len(ids)
+    pot = fly.Generic(data)
+    box = fly.Box(tuple(ex))
+    s1 = fly.System(data, box, ids)
+    rmin, _, failed, _ = fly.LBFGS().minimise(s1, pos, pot)
+    assert not failed[0]
+    rmin = rmin[0]
+    P, A = inputs.perturbed_batch(rmin, ex, N - 1, 64, seed=1334)  # bench.py's batch
+    sR = fly.System(data, box, ids, replicas=64)
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(sR, P, A, rmin, pot)
+    sR.close()
+    assert set(code.tolist()) <= {0, -1, -2, -3}
+    order = [k for k in np.argsort(-cnt[:, 0]) if cnt[k, 0] <= 500]
+    picks = ([k for k in order if code[k] == 0][:5] + [k for k in order if code[k] != 0][:3])[:8]
+    assert len(picks) >= 6
+    tab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(tab, ex)
+    fz = np.zeros(N, np.uint8)
+    o_r, o_ax, o_code, o_cnt = osys.find_sp_batch(P[picks], A[picks], ids, fz, rmin, threads=len(picks))
+    nl = fly.List(s1, data.rcut())
+
+    def energy(r):
+        nl.rebuild(r)
+        return pot.energy(nl)[0]
+
+    e_min = energy(rmin)
+    same, branched = 0, []
+    for j, k in enumerate(picks):
+        if code[k] != o_code[j] or (code[k] == 0 and np.abs(out_r[k] - o_r[j]).max() > 1e-5):
+            branched.append((int(k), int(code[k]), int(o_code[j]), int(cnt[k, 0]), int(o_cnt[j, 0])))
+            continue
+        same += 1
+        if code[k] == 0:
+            assert abs((energy(out_r[k]) - e_min) - (energy(o_r[j]) - e_min)) < 1e-6
+            assert abs(abs((out_ax[k] * o_ax[j]).sum()) - 1) < 1e-3
+    with capsys.disabled():
+        print(f"\n[C2 search parity] {same}/{len(picks)} sampled 16 000-atom searches identical in exit and saddle "
+              f"(GPU evals {cnt[picks, 0].tolist()}, oracle {o_cnt[:, 0].tolist()}); branch-outs {branched}")
+    assert len(branched) <= 1 and all(min(b[3], b[4]) > 150 for b in branched)
+    s1.close()

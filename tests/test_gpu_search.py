@@ -322,3 +322,73 @@ def test_dimer_64_searches_branch_outs_classified(gpu, otab, oracle_lib, capsys)
     assert len(branched) <= R // 10
     # a branch-out only happens on long trajectories: the short ones must all agree
     assert all(min(b[3], b[4]) > 150 for b in branched)
+
+
+def test_queue_refill_equals_batch_equals_single(gpu, small_cell, oracle_lib):
+    """ofly_dimer_find_sp_stream: 24 searches through 5 resident slots (finished slots re-arm on the device), the same 24
+    as one batch of 24, as three shards of 8 (what three GPUs would run) and one by one: bit-identical records. What a
+    search computes depends neither on the batch composition nor on the slot it ran in."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P8, A8 = small_cell
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (5, 3, 3, 4), rep) for rep in range(24)]
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    pot = fly.Generic(data)
+    box = fly.Box(tuple(ex))
+
+    def run(R, p, a):
+        s = fly.System(data, box, ids, fz, replicas=R)
+        try:
+            return fly.Dimer().find_sp(s, p, a, r0, pot)
+        finally:
+            s.close()
+
+    full = run(24, P, A)
+    stream = run(5, P, A)
+    for x, y in zip(full, stream):
+        assert np.array_equal(x, y)
+    from openfly_b200 import shard
+    parts = {}
+    for rank in range(3):
+        mine, (p, a) = shard.shard((P, A), 24, 3, rank)
+        o = run(len(mine), p, a)
+        for k, g in enumerate(mine):
+            parts[int(g)] = tuple(v[k] for v in o)
+    for g in range(24):
+        for x, y in zip(parts[g], (v[g] for v in full)):
+            assert np.array_equal(x, y)
+    for g in (0, 7, 23):
+        one = run(1, P[g:g + 1], A[g:g + 1])
+        for x, y in zip(one, full):
+            assert np.array_equal(x[0], y[g])
+    assert len(set(full[2].tolist())) >= 2  # the set is not trivial: several exit codes
+    # fewer searches than slots
+    few = run(16, P[:3], A[:3])
+    for x, y in zip(few, full):
+        assert np.array_equal(x, y[:3])
+    # minimiser: same contract
+    jit = np.stack([oracle_lib.jitter(base, (9, 2, 3, 40 + r), 0.05) for r in range(7)])
+    s7 = fly.System(data, box, ids, fz, replicas=7)
+    s2 = fly.System(data, box, ids, fz, replicas=2)
+    a7, b7 = fly.LBFGS().minimise(s7, jit, pot), fly.LBFGS().minimise(s2, jit, pot)
+    for x, y in zip(a7, b7):
+        assert np.array_equal(x, y)
+    s7.close(), s2.close()
+
+
+def test_search_graph_is_reused_between_calls(gpu, small_cell):
+    """The instantiated tick graph is kept while the kernel arguments are unchanged: a second identical call gives
+    identical results with and without the cache."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    pot = fly.Generic(data)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
+    a = fly.Dimer().find_sp(s, P, A, r0, pot)
+    b = fly.Dimer().find_sp(s, P, A, r0, pot)
+    os.environ["OFLY_NO_GRAPH_CACHE"] = "1"
+    try:
+        c = fly.Dimer().find_sp(s, P, A, r0, pot)
+    finally:
+        del os.environ["OFLY_NO_GRAPH_CACHE"]
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    s.close()
