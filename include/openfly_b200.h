@@ -222,6 +222,66 @@ int ofly_dimer_find_sp_stream_dev(ofly_batch *b, const ofly_dimer_options *opt, 
                                   const double *hist_sp_dev, long n_hist, double theta_tol, int count_frozen, double *pos_out_dev,
                                   double *axis_out_dev, int *exit_code_dev, long *counters_dev);
 
+/* ---- saddle::Master's per-mechanism numerics, batched over the saddle points of one environment ------------------------ */
+
+/* hessian (eam.cpp:122-233) of EVERY replica in one launch: out [R][(3N)^2], layout as ofly_eam_hessian. */
+int ofly_eam_hessian_batch(ofly_batch *b, int mass_weight, double *hess_host);
+
+typedef struct ofly_mech_options { /* the fields of saddle::Master::Options these steps read, find.hpp:112-184 */
+  double nudge_frac;             /* 0.01 */
+  double basin_tol;              /* 0.05 */
+  double stationary_tol;         /* basin_tol / 2 */
+  double hessian_eigen_zero_tol; /* 1e-6 */
+  long centre;        /* geo[0][i_]: the atom the mechanism must be centred on (find.cpp:1082-1087); < 0: not checked */
+  long freeze_atom;   /* m_sep_list[centre] (ofly_mech_sep_list): frozen during the two relaxations when nothing else is
+                         (find.cpp:1026-1034); < 0: none */
+  int num_zero_modes; /* Master::m_num_zero_modes as ofly_mech_minimum returned it */
+  int skip_pathway;   /* != 0: no relaxations; E0 = energy of in_min, only the saddle's energy / Hessian rules are evaluated */
+} ofly_mech_options;
+void ofly_mech_options_default(ofly_mech_options *o);
+
+typedef enum ofly_mech_status {
+  OFLY_MECH_OK = 0,                    /* a mechanism: min -> sp -> min, first-order saddle */
+  OFLY_MECH_MINIMISATION_FAILED = 1,   /* do_adj_min returns {} (find.cpp:1038-1050) */
+  OFLY_MECH_NOT_CENTRED = 2,           /* largest displacement is not on `centre` (find.cpp:1084) */
+  OFLY_MECH_UNLINKED = 3,              /* |rev - in| > basin_tol (find.cpp:779) */
+  OFLY_MECH_BACK_TO_INITIAL = 4,       /* |fwd - rev| < basin_tol (find.cpp:783) */
+  OFLY_MECH_MIN_TO_SP_TOO_SHORT = 5,   /* |rev - sp| < stationary_tol (find.cpp:787) */
+  OFLY_MECH_SP_TO_MIN_TOO_SHORT = 6,   /* |fwd - sp| < stationary_tol (find.cpp:791) */
+  OFLY_MECH_HIGHER_ORDER_SADDLE = 7,   /* a second negative mode (find.cpp:852-855) */
+  OFLY_MECH_ERR_SP_BELOW_MIN = -1,     /* the reference's verify(Esp > E0) (find.cpp:807) */
+  OFLY_MECH_ERR_NO_NEGATIVE_MODE = -2, /* verify(freq[0] < -tol) (find.cpp:846) */
+  OFLY_MECH_ERR_ZERO_MODES = -3,       /* zero-mode count differs from the minimum's (throw, find.cpp:862-867) */
+  OFLY_MECH_OUT_OF_BOUNDS = -5         /* Spline::OutOfBounds in a relaxation, an energy or the Hessian */
+} ofly_mech_status;
+
+typedef struct ofly_mech_record {
+  int status;      /* ofly_mech_status */
+  int count_zeros; /* zero modes of the saddle's mass-weighted Hessian */
+  double i2r, r2f, r2w, w2f; /* |rev - in|, |fwd - rev|, |rev - sp|, |fwd - sp| (find.cpp:772-775) */
+  double E0, Esp, Ef;        /* energies of rev, sp, fwd (find.cpp:797-805) */
+  double barrier, delta;     /* Esp - E0, Ef - E0 */
+  double log_prod_eigen;     /* sum of log(lambda) over modes 1.. above the tolerance: what Mechanism::kinetic_pre holds
+                                before find.cpp:287; ofly_mech_prefactor turns it into the attempt frequency */
+  double min_mode;           /* freq[0] */
+} ofly_mech_record;
+
+/* m_sep_list (find.cpp:223-244): for every atom the index of the atom furthest away under the minimum image. pos: [3N], out: [N]. */
+int ofly_mech_sep_list(ofly_batch *b, const double *pos_host, int *sep_host);
+/* Master::calc_minima_hess (find.cpp:1094-1144): mass-weighted Hessian of the minimum, its eigenvalues (eig_host: [3N] or NULL),
+ * sum of log over the non-zero modes, zero-mode count; OFLY_ERR_INVALID with the reference's message for a negative mode or an
+ * unexpected zero-mode count (the outputs are still written). */
+int ofly_mech_minimum(ofly_batch *b, const double *in_min_host, double zero_tol, double *log_prod_eigen, int *num_zero_modes,
+                      int *count_frozen, double *eig_host);
+/* do_adj_min + the numeric half of saddle_2_mech (find.cpp:1014-1090, 757-871) for n_saddles dimer results at once.
+ * sp / axis: [S][3N] as Dimer::find_sp returned them; in_min: [3N]. rev / sp_out / fwd: [S][3N] drift-corrected pathway
+ * (may be NULL). records: [S]. Uses b's R slots for energies / Hessians and a sibling batch for the relaxations. */
+int ofly_mech_from_saddles(ofly_batch *b, const ofly_mech_options *opt, const ofly_lbfgs_options *min_opt, long n_saddles,
+                           const double *sp_host, const double *axis_host, const double *in_min_host, double *rev_host,
+                           double *sp_out_host, double *fwd_host, ofly_mech_record *records);
+/* find.cpp:287: sqrt(exp(log_prod_eigen_min - log_prod_eigen_sp) / (2 pi 1.6605390666050e-27)), in Hz. */
+double ofly_mech_prefactor(double log_prod_eigen_min, double log_prod_eigen_sp);
+
 /* Measurement aid (bench.py): FP64 FMA instructions per second this device sustains on register-only chains. */
 int ofly_bench_fp64_fma(ofly_ctx *ctx, int iters, double *fma_per_s);
 

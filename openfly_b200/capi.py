@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libopenfly_b200.so")
+LIB_PATH = os.environ.get("OFLY_LIB") or os.path.join(_PKG, "libopenfly_b200.so")  # OFLY_LIB: a tuning build (csrc/Makefile VARIANT=)
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "openfly_b200.h")
 
 OFLY_OK, OFLY_ERR_INVALID, OFLY_ERR_OUT_OF_BOUNDS, OFLY_ERR_CUDA, OFLY_ERR_CAPACITY = range(5)
@@ -52,6 +52,18 @@ class DimerOptions(C.Structure):
 class RotorOptions(C.Structure):
     _fields_ = [("n", C.c_int), ("iter_max_rot", C.c_int), ("relax_in_convex", C.c_int), ("delta_r", C.c_double),
                 ("theta_tol", C.c_double)]
+
+
+class MechOptions(C.Structure):
+    _fields_ = [("nudge_frac", C.c_double), ("basin_tol", C.c_double), ("stationary_tol", C.c_double),
+                ("hessian_eigen_zero_tol", C.c_double), ("centre", C.c_long), ("freeze_atom", C.c_long), ("num_zero_modes", C.c_int),
+                ("skip_pathway", C.c_int)]
+
+
+class MechRecord(C.Structure):
+    _fields_ = [("status", C.c_int), ("count_zeros", C.c_int), ("i2r", C.c_double), ("r2f", C.c_double), ("r2w", C.c_double),
+                ("w2f", C.c_double), ("E0", C.c_double), ("Esp", C.c_double), ("Ef", C.c_double), ("barrier", C.c_double),
+                ("delta", C.c_double), ("log_prod_eigen", C.c_double), ("min_mode", C.c_double)]
 
 
 # symbol -> (restype, argtypes); the test-suite checks this table against the header.
@@ -109,6 +121,13 @@ SIGNATURES = {
     "ofly_dimer_find_sp_stream_dev": (C.c_int, [_vp, C.POINTER(DimerOptions), C.POINTER(RotorOptions), C.c_long, _vp, _vp, _vp, _vp,
                                                 C.c_long, C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
     "ofly_eam_hessian_eigenvalues": (C.c_int, [_vp, C.c_long, C.c_int, _dp]),
+    "ofly_eam_hessian_batch": (C.c_int, [_vp, C.c_int, _dp]),
+    "ofly_mech_options_default": (None, [C.POINTER(MechOptions)]),
+    "ofly_mech_sep_list": (C.c_int, [_vp, _dp, _ip]),
+    "ofly_mech_minimum": (C.c_int, [_vp, _dp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
+    "ofly_mech_from_saddles": (C.c_int, [_vp, C.POINTER(MechOptions), C.POINTER(LbfgsOptions), C.c_long, _dp, _dp, _dp, _dp, _dp, _dp,
+                                         C.POINTER(MechRecord)]),
+    "ofly_mech_prefactor": (C.c_double, [C.c_double, C.c_double]),
     "ofly_bench_fp64_fma": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "ofly_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "ofly_dev_free": (C.c_int, [_vp, _vp]),

@@ -25,10 +25,23 @@ namespace ofly {
 
   // Row entries are a pure stream (read once per pass, 0.4 GB per pass at C2): evict-first in L2 so that the 33 MB of
   // position records and the 2.9 MB of tables, which every SM gathers from, stay resident.
+#ifndef OFLY_ROW_LOAD
+#define OFLY_ROW_LOAD 1
+#endif
   __device__ __forceinline__ uint32_t ld_row(const uint32_t *p) {
+#if OFLY_ROW_LOAD == 0
+    return __ldg(p);
+#elif OFLY_ROW_LOAD == 1
     uint32_t v;
     asm("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+#else
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint32_t v;
+    asm("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#endif
   }
 
   // Decode one neighbour entry and fetch its record.
@@ -43,9 +56,16 @@ namespace ofly {
       int dxg = code % 3, dyg = (code / 3) % 3, dzg = code / 9;
       sx = shift_of(dxg, B.box.L[0]), sy = shift_of(dyg, B.box.L[1]), sz = shift_of(dzg, B.box.L[2]);
     }
-    g.dx = (pj.x + sx) - pi.x;
-    g.dy = (pj.y + sy) - pi.y;
-    g.dz = (pj.z + sz) - pi.z;
+#ifdef OFLY_SHIFT_BRANCH
+    if (code == kShiftCentre) {  // most pairs: no image arithmetic ((x + 0.0) - y == x - y, same bits)
+      g.dx = pj.x - pi.x, g.dy = pj.y - pi.y, g.dz = pj.z - pi.z;
+    } else
+#endif
+    {
+      g.dx = (pj.x + sx) - pi.x;
+      g.dy = (pj.y + sy) - pi.y;
+      g.dz = (pj.z + sz) - pi.z;
+    }
     g.r2 = fma(g.dz, g.dz, fma(g.dy, g.dy, g.dx * g.dx));
     g.fprime_j = pj.w;
     return g;
@@ -57,6 +77,16 @@ namespace ofly {
   // negative nor a NaN argument can index outside the table.
   __device__ __forceinline__ int knot_index(double x, double inv_dx, double dx, int n_knots, double &x0, bool &oob) {
     const double s = x * inv_dx;
+#ifdef OFLY_KNOT_INT
+    // the same test on the integer pipe (the FP64 pipe is the co-limiter): cvt.rzi saturates, so s <= -1 gives i < 0 and
+    // s >= n_knots gives i >= n_knots; NaN / Inf are caught by their exponent bits
+    int i = __double2int_rz(s);
+    if ((unsigned)i >= (unsigned)n_knots || (__double2hiint(s) & 0x7ff00000) == 0x7ff00000) {
+      oob = true;
+      i = i > 0 ? n_knots - 1 : 0;
+      if ((__double2hiint(s) & 0x7ff00000) == 0x7ff00000) i = 0;
+    }
+#else
     int i = 0;
     if (s > -1.0 && s < (double)n_knots) {
       i = __double2int_rz(s);
@@ -64,6 +94,7 @@ namespace ofly {
       oob = true;
       i = s > 0.0 ? n_knots - 1 : 0;  // NaN lands on 0
     }
+#endif
     x0 = fma(-(double)i, dx, x);
     return i;
   }
@@ -80,6 +111,11 @@ namespace ofly {
   // trajectory do not depend on how many replicas share its batch (the tick kernels pick G from the active count) or on
   // how a batch is sharded over GPUs.
   constexpr int kVirt = 16;
+#ifdef OFLY_PLAIN_SUM  // tuning only: one accumulator per lane (the sums then depend on the sub-warp width)
+#define OFLY_VJ(j) 0
+#else
+#define OFLY_VJ(j) (j)
+#endif
 
   template <int G, int NS>
   struct VirtSum {
@@ -128,10 +164,10 @@ namespace ofly {
             double rr = g.r2 * fast_rsqrt(g.r2);
             double x0;
             int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
-            acc.a[j][0] += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
+            acc.a[OFLY_VJ(j)][0] += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
             if (WITH_V) {
               int hi = max(ti, g.tj), lo = min(ti, g.tj);
-              acc.a[j][1] += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+              acc.a[OFLY_VJ(j)][1] += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
             }
           }
         }
@@ -173,7 +209,8 @@ namespace ofly {
             mag = fma(Fi, p_ji, mag);
             mag = fma(g.fprime_j, p_ij, mag);
             double s = mag * rinv;
-            acc.a[j][0] = fma(-s, g.dx, acc.a[j][0]), acc.a[j][1] = fma(-s, g.dy, acc.a[j][1]), acc.a[j][2] = fma(-s, g.dz, acc.a[j][2]);
+            acc.a[OFLY_VJ(j)][0] = fma(-s, g.dx, acc.a[OFLY_VJ(j)][0]), acc.a[OFLY_VJ(j)][1] = fma(-s, g.dy, acc.a[OFLY_VJ(j)][1]),
+            acc.a[OFLY_VJ(j)][2] = fma(-s, g.dz, acc.a[OFLY_VJ(j)][2]);
           }
         }
       }

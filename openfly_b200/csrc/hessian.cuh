@@ -4,11 +4,15 @@
 // frozen rows/columns left zero.
 //
 //   pass 1  rho_b and mu_b = -sum_a phi'_{a->b}(r) dr / r                       (eam.cpp:129-143)
-//   pass 2  one warp per column block z: the (z,a) pair terms are computed redundantly on all lanes
-//           (uniform loop over a), the 9 elements of the diagonal block are kept in registers, the
-//           off-diagonal block (a,z) is added by 9 lanes, and the neighbour-of-neighbour overlap terms
-//           (z - a - g) are spread over the 32 lanes. Different paths reach the same block (g,z), so
-//           contributions are combined with fp64 atomic adds (RED.ADD.F64 in L2).
+//   pass 2  one warp per column block z (the reference's ownership, eam.cpp:165-232: everything pass 2 writes for z
+//           lies in columns 3z..3z+2): the (z,a) pair terms are computed redundantly on all lanes (uniform loop over
+//           a), the 9 elements of the diagonal block are kept in registers, the off-diagonal block (a,z) is added
+//           by 9 lanes, and the neighbour-of-neighbour overlap terms (z - a - g) are spread over the 32 lanes.
+//           Different paths reach the same block (g,z), but always from the SAME warp, so there are no atomics:
+//           plain read-modify-writes, ordered by __syncwarp() between the steps of the loop over a; lanes that hit
+//           the same block inside one step (the same real atom g through two periodic images) add one after the
+//           other in lane order. The sum order is fixed, so the matrix is bit-reproducible.
+// Batched: one launch assembles the Hessians of `count` replicas (selection list), matrix s at H + s * stride.
 // This is assembly into a dense matrix (a scatter by nature); it runs once per successful search,
 // not inside the search loop.
 #pragma once
@@ -18,12 +22,16 @@
 namespace ofly {
 
   // aux layout: [N][4] = {rho, mu_x, mu_y, mu_z}
+  // aux of selected replica s starts at aux + s * 4 N
   template <int G>
-  static __global__ void __launch_bounds__(256) k_hess_rho_mu(BatchDev B, TablesDev T, int r, double *__restrict__ aux) {
+  static __global__ void __launch_bounds__(256) k_hess_rho_mu(BatchDev B, TablesDev T, const int *__restrict__ sel, int count,
+                                                              double *__restrict__ aux_all) {
     size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
     int lane = threadIdx.x % G;
-    if (g >= (size_t)B.N) return;
-    int i = (int)g;
+    if (g >= (size_t)B.N * count) return;
+    const int s = (int)(g / B.N), r = sel[s];
+    int i = (int)(g % B.N);
+    double *aux = aux_all + (size_t)s * 4 * B.N;
     const double4 *pos = B.pos4 + (size_t)r * B.N;
     const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
     const int n = B.cnt[(size_t)r * B.N + i];
@@ -58,26 +66,31 @@ namespace ofly {
     fp = spline_fp(k, x0), fpp = spline_fpp(k, x0);
   }
 
-  // H(3*bi + row, 3*bj + col) += s * u[row] * v[col] for the 9 (row, col) of a block.
-  __device__ __forceinline__ void atomic_outer(double *H, size_t n3, int bi, int bj, double s, const double u[3], const double v[3]) {
+  // H(3*bi + row, 3*bj + col) += s * u[row] * v[col] for the 9 (row, col) of a block (plain read-modify-write: the
+  // calling warp owns the column block).
+  __device__ __forceinline__ void add_outer(double *H, size_t n3, int bi, int bj, double s, const double u[3], const double v[3]) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
 #pragma unroll
       for (int rw = 0; rw < 3; rw++) {
-        atomicAdd(H + (size_t)(3 * bj + c) * n3 + (size_t)(3 * bi + rw), s * u[rw] * v[c]);
+        double *p = H + (size_t)(3 * bj + c) * n3 + (size_t)(3 * bi + rw);
+        *p = *p + s * u[rw] * v[c];
       }
     }
   }
 
   template <int G>
-  static __global__ void __launch_bounds__(256) k_hess_columns(BatchDev B, TablesDev T, int r, const double *__restrict__ aux,
-                                                        double *__restrict__ H) {
+  static __global__ void __launch_bounds__(256) k_hess_columns(BatchDev B, TablesDev T, const int *__restrict__ sel, int count,
+                                                               const double *__restrict__ aux_all, double *__restrict__ H_all, size_t h_stride) {
     static_assert(G == 32, "one full warp per column block");
     size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G;
     int lane = threadIdx.x % G;
-    if (w >= (size_t)B.N) return;
-    int z = (int)w;
+    if (w >= (size_t)B.N * count) return;
+    const int s = (int)(w / B.N), r = sel[s];
+    int z = (int)(w % B.N);
     if (B.frozen[z]) return;
+    const double *aux = aux_all + (size_t)s * 4 * B.N;
+    double *H = H_all + (size_t)s * h_stride;
 
     const size_t n3 = 3 * (size_t)B.N;
     const double4 *pos = B.pos4 + (size_t)r * B.N;
@@ -100,7 +113,7 @@ namespace ofly {
 
     for (int k = 0; k < n_z; k++) {
       PairGeom p = load_pair(B, pos, pz, row_z[k]);
-      if (!(p.r2 < T.r_cut_sq)) continue;
+      if (!(p.r2 < T.r_cut_sq)) continue;  // warp-uniform
       const int a = p.j, ta = p.tj;
       double rinv = fast_rsqrt(p.r2);
       double rr = p.r2 * rinv;
@@ -134,8 +147,10 @@ namespace ofly {
         int rw = lane % 3, c = lane / 3;
         double v = -BArr * dr[rw] * dr[c] + ur * dr[rw] * mu_z[c] - ru * mu_a[rw] * dr[c];
         if (rw == c) v -= A;
-        atomicAdd(H + (size_t)(3 * z + c) * n3 + (size_t)(3 * a + rw), v);
+        double *q = H + (size_t)(3 * z + c) * n3 + (size_t)(3 * a + rw);
+        *q = *q + v;
       }
+      __syncwarp();  // the direct block is in memory before an overlap term may add to it (a's row can hold a's own image)
 
       // overlap terms z - a - g
       double ddFg = Fpp_a * pza;
@@ -143,24 +158,40 @@ namespace ofly {
       // neighbours of a are relative to the *real* atom a: dr_ag is image-independent
       const uint32_t *row_a = B.nbr + ((size_t)r * B.N + a) * B.K;
       const int n_a = B.cnt[(size_t)r * B.N + a];
-      for (int q = lane; q < n_a; q += G) {
-        PairGeom pg = load_pair(B, pos, pa_real, row_a[q]);
-        if (!(pg.r2 < T.r_cut_sq)) continue;
-        int g = pg.j;
-        bool take = (g > z && !B.frozen[g]);
-        if (g == z) {
-          double sx = p.dx + pg.dx, sy = p.dy + pg.dy, sz = p.dz + pg.dz;
-          take = sqrt(fma(sz, sz, fma(sy, sy, sx * sx))) > 1e-6;  // a periodic image of z itself (eam.cpp:223)
+      for (int q0 = 0; q0 < n_a; q0 += G) {  // warp-uniform trip count
+        const int q = q0 + lane;
+        bool take = false;
+        int g = -1;
+        double mag = 0;
+        double dag[3] = {0, 0, 0};
+        if (q < n_a) {
+          PairGeom pg = load_pair(B, pos, pa_real, row_a[q]);
+          if (pg.r2 < T.r_cut_sq) {
+            g = pg.j;
+            take = (g > z && !B.frozen[g]);
+            if (g == z) {
+              double sx = p.dx + pg.dx, sy = p.dy + pg.dy, sz = p.dz + pg.dz;
+              take = sqrt(fma(sz, sz, fma(sy, sy, sx * sx))) > 1e-6;  // a periodic image of z itself (eam.cpp:223)
+            }
+            if (take) {
+              double rinv_ag = fast_rsqrt(pg.r2);
+              double r_ag = pg.r2 * rinv_ag;
+              double y0;
+              int idg = knot_index(r_ag, T.inv_dR, T.dR, T.kR, y0, oob);
+              double pga = spline_fp(ld256_nc(T.phi + (size_t)(pg.tj + T.n_types * ta) * T.kR + idg), y0);  // phi(g -> a)
+              mag = ddFg * rinv * rinv_ag * pga;
+              dag[0] = pg.dx, dag[1] = pg.dy, dag[2] = pg.dz;
+            }
+          }
         }
-        if (!take) continue;
-        double rinv_ag = fast_rsqrt(pg.r2);
-        double r_ag = pg.r2 * rinv_ag;
-        double y0;
-        int idg = knot_index(r_ag, T.inv_dR, T.dR, T.kR, y0, oob);
-        double pga = spline_fp(ld256_nc(T.phi + (size_t)(pg.tj + T.n_types * ta) * T.kR + idg), y0);  // phi(g -> a)
-        double mag = ddFg * rinv * rinv_ag * pga;
-        const double dag[3] = {pg.dx, pg.dy, pg.dz};
-        atomic_outer(H, n3, g, z, -mag, dag, dr);
+        // lanes that target the same block (g reached through two images) take turns in lane order
+        const unsigned peers = __match_any_sync(0xffffffffu, take ? g : -1 - lane);
+        const int turn = __popc(peers & ((1u << lane) - 1u));
+        const int turns = __reduce_max_sync(0xffffffffu, take ? __popc(peers) : 0);
+        for (int t = 0; t < turns; t++) {
+          if (take && turn == t) add_outer(H, n3, g, z, -mag, dag, dr);
+          __syncwarp();
+        }
       }
     }
     if (lane < 9) {
@@ -171,19 +202,22 @@ namespace ofly {
 #pragma unroll
         for (int j = 0; j < 3; j++)
           if (i == rw && j == c) v = D[i][j];
-      atomicAdd(H + (size_t)(3 * z + c) * n3 + (size_t)(3 * z + rw), v);
+      double *q = H + (size_t)(3 * z + c) * n3 + (size_t)(3 * z + rw);
+      *q = *q + v;
     }
     if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
   }
 
-  // Hessian::mass_weight (hessian.hpp:136-143): every element scaled by 1/sqrt(m_row m_col).
-  static __global__ void k_hess_mass_weight(double *__restrict__ H, int N, const uint8_t *__restrict__ type, const double *__restrict__ mass) {
+  // Hessian::mass_weight (hessian.hpp:136-143): every element scaled by 1/sqrt(m_row m_col); `count` matrices, h_stride apart.
+  static __global__ void k_hess_mass_weight(double *__restrict__ H_all, size_t h_stride, int count, int N, const uint8_t *__restrict__ type,
+                                            const double *__restrict__ mass) {
     size_t n3 = 3 * (size_t)N;
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n3 * n3) return;
     size_t col = t / n3, rw = t % n3;
     double mi = mass[type[col / 3]];
-    H[t] *= 1 / sqrt(mi * mass[type[rw / 3]]);
+    const double f = 1 / sqrt(mi * mass[type[rw / 3]]);
+    for (int s = 0; s < count; s++) H_all[(size_t)s * h_stride + t] *= f;
   }
 
 }  // namespace ofly

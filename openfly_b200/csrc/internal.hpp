@@ -54,7 +54,16 @@ struct ofly_ctx {
   cudaStream_t stream = nullptr;
   long launches = 0;
   long ticks = 0;  // search ticks executed (search.cuh)
-  void *cusolver = nullptr;  // cusolverDnHandle_t, created on the first dense eigenvalue solve
+  // dense eigenvalue solves: a few independent cuSOLVER lanes (handle + stream + workspace), created on first use
+  struct SolverLane {
+    void *handle = nullptr;  // cusolverDnHandle_t
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    ofly::DevBuf<double> work;
+    ofly::DevBuf<int> info;
+  };
+  std::vector<SolverLane> solver;
+  cudaEvent_t solver_fork = nullptr;
   int sm_count = 0;
   int max_smem_optin = 0;
 };
@@ -100,8 +109,11 @@ struct ofly_batch {
   ofly::DevBuf<double> stage_a, stage_b, stage_c, scratch;  // [R][3N] staging for the host-pointer entry points
   ofly::DevBuf<char> search_ws;                              // workspace of the search engine
   ofly::DevBuf<double> hess_H, hess_aux, hess_mass, hess_work, hess_eig;  // dense Hessian path, kept between calls
-  ofly::DevBuf<int> hess_info;
+  ofly::DevBuf<int> hess_info, hess_sel;
+  std::vector<uint8_t> frozen_host;
   std::vector<ofly::DevBuf<char>> io_pool;                   // device staging of the host-pointer search calls
   std::vector<int> fault_host;
   ofly_search_graph search_graph;
+  ofly_batch *sibling = nullptr;  // same system with one more frozen atom (mech_api.cu: the relaxations of do_adj_min)
+  long sibling_atom = -1;
 };

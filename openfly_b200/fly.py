@@ -21,7 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import capi
-from .capi import DimerOptions, LbfgsOptions, OflyError, OutOfBounds, RotorOptions, check, f64, ptr  # noqa: F401
+from .capi import DimerOptions, LbfgsOptions, MechOptions, MechRecord, OflyError, OutOfBounds, RotorOptions, check, f64, ptr  # noqa: F401
 
 _dp, _ip, _lp, _u32p, _u8p = capi._dp, capi._ip, capi._lp, capi._u32p, capi._u8p
 
@@ -270,6 +270,13 @@ class Generic:
         check(nl.sys.ctx.lib.ofly_eam_hessian(nl.sys.h, replica, 1 if mass_weight else 0, ptr(out, _dp)))
         return out.T.copy()  # the library writes column-major
 
+    def hessian_batch(self, nl: List, mass_weight: bool = False) -> np.ndarray:
+        """[R, 3N, 3N]: the Hessians of every replica from one launch (lower triangles meaningful)."""
+        n3 = 3 * nl.sys.N
+        out = np.zeros((nl.sys.R, n3, n3), dtype=np.float64)
+        check(nl.sys.ctx.lib.ofly_eam_hessian_batch(nl.sys.h, 1 if mass_weight else 0, ptr(out, _dp)))
+        return np.ascontiguousarray(out.transpose(0, 2, 1))  # the library writes column-major
+
     def hessian_eigenvalues(self, nl: List, replica: int = 0, mass_weight: bool = True) -> np.ndarray:
         """system::Hessian::eigenvalues() of the (mass-weighted) Hessian, solved on the device: only 3N doubles return."""
         out = np.zeros(3 * nl.sys.N, dtype=np.float64)
@@ -360,7 +367,89 @@ class Dimer:
         return out_r, out_ax, code, cnt
 
 
-# ---- Vineyard prefactor from mass-weighted Hessians (host side: the dense eigensolve is SURVEY.md 8(f2), not on the GPU) ----
+def mech_options(**kw) -> MechOptions:
+    o = MechOptions()
+    capi.load().ofly_mech_options_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Mechanisms:
+    """The numerics of saddle::Master that follow the dimer searches of one environment (src/saddle/find.cpp), batched on
+    the device: calc_minima_hess (:1094-1144), m_sep_list (:223-244), do_adj_min (:1014-1090), the energy / Hessian /
+    eigenvalue half of saddle_2_mech (:757-871) and the prefactor (:287). Thin callers of the ofly_mech_* C entry points."""
+
+    FIELDS = ("status", "count_zeros", "i2r", "r2f", "r2w", "w2f", "E0", "Esp", "Ef", "barrier", "delta", "log_prod_eigen", "min_mode")
+
+    def __init__(self, data: DataEAM, box: Box, type_id, frozen=None, replicas: int = 64):
+        self.sys = System(data, box, type_id, frozen, replicas=replicas)
+        self.lib = data.ctx.lib
+        self.log_prod_eigen = None
+        self.num_zero_modes = None
+
+    def close(self) -> None:
+        self.sys.close()
+
+    def sep_list(self, positions) -> np.ndarray:
+        p = f64(positions).reshape(self.sys.N, 3)
+        out = np.zeros(self.sys.N, dtype=np.int32)
+        check(self.lib.ofly_mech_sep_list(self.sys.h, ptr(p, _dp), ptr(out, _ip)))
+        return out
+
+    def minimum(self, in_min, zero_tol: float = 1e-6):
+        """calc_minima_hess: returns (sum log lambda, zero modes, frozen atoms, eigenvalues[3N]) and remembers the first two."""
+        p = f64(in_min).reshape(self.sys.N, 3)
+        lp, nz, nf = C.c_double(), C.c_int(), C.c_int()
+        eig = np.zeros(3 * self.sys.N)
+        check(self.lib.ofly_mech_minimum(self.sys.h, ptr(p, _dp), zero_tol, C.byref(lp), C.byref(nz), C.byref(nf), ptr(eig, _dp)))
+        self.log_prod_eigen, self.num_zero_modes = lp.value, nz.value
+        return lp.value, nz.value, nf.value, eig
+
+    def _run(self, opt, lopt, in_min, sp, axis, want_path):
+        N = self.sys.N
+        p = f64(sp).reshape(-1, N, 3)
+        S = p.shape[0]
+        ax = None if axis is None else f64(axis).reshape(S, N, 3)
+        mn = f64(in_min).reshape(N, 3)
+        rec = (MechRecord * S)()
+        outs = [np.zeros_like(p) for _ in range(3)] if want_path else [None] * 3
+        arg = [ptr(o, _dp) if o is not None else None for o in outs]
+        check(self.lib.ofly_mech_from_saddles(self.sys.h, C.byref(opt), C.byref(lopt), S, ptr(p, _dp), None if ax is None else ptr(ax, _dp),
+                                              ptr(mn, _dp), arg[0], arg[1], arg[2], rec))
+        res = {k: np.array([getattr(r, k) for r in rec]) for k in self.FIELDS}
+        if want_path:
+            res["rev"], res["sp"], res["fwd"] = outs
+        return res
+
+    def from_saddles(self, in_min, sp, axis, centre: int = -1, freeze_atom: int = -1, opt: MechOptions | None = None,
+                     min_opt: LbfgsOptions | None = None):
+        """do_adj_min + saddle_2_mech numerics for S dimer results (sp, axis: [S, N, 3]). Returns a dict of per-saddle arrays
+        (ofly_mech_record fields, `prefactor` in Hz for status 0) plus the drift-corrected pathway rev / sp / fwd."""
+        if self.num_zero_modes is None:
+            self.minimum(in_min)
+        o = opt or mech_options()
+        o.centre, o.freeze_atom, o.num_zero_modes, o.skip_pathway = centre, freeze_atom, self.num_zero_modes, 0
+        res = self._run(o, min_opt or lbfgs_options(), in_min, sp, axis, True)
+        res["prefactor"] = np.array([self.lib.ofly_mech_prefactor(self.log_prod_eigen, lp) if st == 0 else np.nan
+                                     for st, lp in zip(res["status"], res["log_prod_eigen"])])
+        return res
+
+    def prefactors(self, in_min, sp, opt: MechOptions | None = None):
+        """Only the Hessian half: barrier against in_min, eigenvalue rules and prefactor of every saddle in sp [S, N, 3].
+        `valid` is 1 where the saddle is first order with the minimum's zero-mode count."""
+        if self.num_zero_modes is None:
+            self.minimum(in_min)
+        o = opt or mech_options()
+        o.num_zero_modes, o.skip_pathway = self.num_zero_modes, 1
+        res = self._run(o, lbfgs_options(), in_min, sp, None, False)
+        res["valid"] = (res["status"] == 0).astype(np.int32)
+        res["prefactor"] = np.array([self.lib.ofly_mech_prefactor(self.log_prod_eigen, lp) if st == 0 else np.nan
+                                     for st, lp in zip(res["status"], res["log_prod_eigen"])])
+        return res
+
+
+# ---- Vineyard prefactor from eigenvalues on the host (numpy): the checker of ofly_mech_* in the tests ----
 
 def hessian_eigenvalues(hess_lower: np.ndarray) -> np.ndarray:
     """system::Hessian::eigenvalues (hessian.hpp:86-93): ascending eigenvalues of the symmetric matrix whose LOWER

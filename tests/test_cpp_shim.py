@@ -101,3 +101,66 @@ def test_cpp_host_shards_replicas_over_devices(demo, oracle_lib, tmp_path):
         for k in range(R):
             if o_code[k] == 0:
                 assert np.abs(sp[k] - o_r[k]).max() < 1e-5
+
+
+SURF = os.path.join(ROOT, "examples", "libfly_surface")
+
+
+def test_libfly_surface_compiles_with_reference_signatures(demo):
+    """include/openfly_b200/libfly.hpp: namespace fly, the reference's own signatures over system::SoA views
+    (generic.hpp:79-136, list.hpp:86-161, lbfgs.hpp:96-118, dimer.hpp:148-155). The forwarding bodies INTEGRATION.md quotes are
+    the ones compiled here."""
+    d = json.loads(subprocess.run([SURF, "--compile-only"], check=True, capture_output=True, text=True).stdout)
+    assert d == {"lbfgs_n": 10, "dimer_n": 10, "rotor_n": 6, "view_sees_owner": 1}
+    text = open(os.path.join(ROOT, "include", "openfly_b200", "libfly.hpp")).read()
+    for sig in ("auto energy(system::SoA<TypeID const &, Frozen const &> in, neigh::List const &nl, int /*threads*/ = 1) -> double",
+                "auto rebuild(system::SoA<Position const &> positions, int num_threads = 1) -> void",
+                "auto update(system::SoA<Delta const &> x) -> void",
+                "auto minimise(system::SoA<Position &, PotentialGradient &> out, system::SoA<Position const &, TypeID const &, Frozen const &> in,",
+                "auto find_sp(system::SoA<Position &, Axis &> out, system::SoA<Position const &, Axis const &, TypeID const &, Frozen const &> in,"):
+        assert sig in text, sig
+
+
+@pytest.mark.gpu
+def test_libfly_surface_matches_oracle(demo, oracle_lib, tmp_path):
+    """A libfly-style program through the reference signatures: energy / gradient / Hessian / for_neighbours / minimise /
+    find_sp (single and batched) against the CPU oracle; two Lists do not disturb each other."""
+    cells, R = 4, 4
+    base, ex, ids = bcc_vacancy(cells, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    tab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(tab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=4)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(R)]
+    path = tmp_path / "starts.bin"
+    np.stack([np.stack([s[0], s[1]]) for s in starts]).astype(np.float64).tofile(path)
+    res = subprocess.run([SURF, WEN, str(cells), str(R), str(path)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    d = json.loads(res.stdout)
+    osys.rebuild(tab.rcut, base)
+    E = osys.energy(ids)
+    assert d["atoms"] == len(ids)
+    assert abs(d["energy"] - E) <= 1e-10 * abs(E)
+    assert abs(d["grad_max"] - np.abs(osys.gradient(ids, fz)).max()) < 1e-9
+    counts = osys.export()[0]
+    assert d["neigh0"] == len(osys.for_neighbours(0, tab.rcut)[0]) and d["pairs"] == int(counts.sum())
+    H = osys.hessian(ids, fz, 4)
+    assert abs(d["h00"] - H[0, 0]) < 1e-9 and abs(d["h30"] - H[3, 0]) < 1e-9
+    assert d["energy_again"] == d["energy"] and d["energy_other_list"] != d["energy"]  # Lists own their state
+    assert d["energy_updated"] != d["energy"] and abs(d["energy_back"] - d["energy"]) < 1e-9
+    assert d["min_failed"] == 0
+    osys.rebuild(tab.rcut, r0)
+    assert abs(d["energy_min"] - osys.energy(ids)) < 1e-9
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    # the program searches from ITS relaxed minimum (1e-6 A from the oracle's): same exits, same saddles
+    o_r, _, o_code, _ = osys.find_sp_batch(P, A, ids, fz, r0, threads=4)
+    assert d["exits"] == o_code.tolist() and d["exit0"] == o_code[0]
+    assert d["single_vs_batch_sp"] == 0.0  # the single-system signature and the batch give the same bits
+    out = np.fromfile(str(path) + ".fly", dtype=np.float64)
+    n3 = 3 * len(ids)
+    assert np.abs(out[:n3].reshape(-1, 3) - r0).max() < 1e-6
+    sp = out[n3:].reshape(R, -1, 3)
+    for k in range(R):
+        if o_code[k] == 0:
+            assert np.abs(sp[k] - o_r[k]).max() < 1e-5

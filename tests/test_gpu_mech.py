@@ -1,0 +1,148 @@
+"""GPU parity of the batched post-search numerics (ofly_mech_*: do_adj_min, saddle_2_mech's energies / Hessian / eigenvalue
+rules, calc_minima_hess, prefactor -- src/saddle/find.cpp) against the CPU composition in tests/mech_oracle.py, on the real
+apps/hydrogen-sized cell (431 atoms). Tolerances are BASELINE.json's: barriers 1e-6 eV, prefactors 1e-4 relative."""
+import numpy as np
+import pytest
+
+from tests import mech_oracle as MO
+from tests.common import WEN, bcc_vacancy, golden_cell
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from openfly_b200 import fly
+
+    ctx = fly.Context(0)
+    data = fly.DataEAM(ctx, WEN)
+    yield fly, ctx, data
+    data.close()
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def c3(gpu, oracle_lib):
+    """The C3 cell, its minimum and the saddles of 64 searches (GPU), shared by the tests below."""
+    fly, ctx, data = gpu
+    otab = oracle_lib.Tables(WEN)
+    base, ex, ids = bcc_vacancy(6, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    osys = oracle_lib.System(otab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=8)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(64)]
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    sR = fly.System(data, fly.Box(tuple(ex)), ids, replicas=64)
+    out_r, out_ax, code, cnt = fly.Dimer().find_sp(sR, P, A, r0, fly.Generic(data))
+    sR.close()
+    ok = np.nonzero(code == 0)[0]
+    assert len(ok) >= 20
+    return otab, osys, ex, ids, fz, r0, out_r[ok], out_ax[ok]
+
+
+def test_batched_hessians_equal_single_and_are_reproducible(gpu, oracle_lib):
+    """One launch for every replica (no atomics, fixed sum order): equal to the per-replica call bit for bit, twice the same bits,
+    and 1e-9 against the oracle."""
+    fly, ctx, data = gpu
+    pos, ex, ids = bcc_vacancy(4, a=2.855, remove=(1,), jitter=0.04, hydrogen=True)
+    R = 3
+    P = np.stack([pos, pos + 0.01 * np.sin(np.arange(pos.size).reshape(pos.shape)), pos[::-1][::-1] * 1.0])
+    fz = np.zeros(len(ids), np.uint8)
+    fz[7] = 1
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=R)
+    nl = fly.List(s, data.rcut())
+    nl.rebuild(P)
+    pot = fly.Generic(data)
+    Hb = pot.hessian_batch(nl)
+    assert np.array_equal(Hb, pot.hessian_batch(nl))
+    for r in range(R):
+        assert np.array_equal(np.tril(Hb[r]), np.tril(pot.hessian(nl, replica=r)))
+    otab = oracle_lib.Tables(WEN)
+    osys = oracle_lib.System(otab, ex)
+    osys.rebuild(otab.rcut, P[1], 4)
+    Ho = osys.hessian(ids, fz, 4)
+    assert np.abs(np.tril(Hb[1]) - np.tril(Ho)).max() < 1e-9
+    assert np.all(Hb[1][21:24, :] == 0) and np.all(Hb[1][:, 21:24] == 0)  # frozen atom: zero rows / columns
+    s.close()
+
+
+def test_minimum_rules_and_sep_list(gpu, c3):
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    mech = fly.Mechanisms(data, fly.Box(tuple(ex)), ids, replicas=8)
+    lp, nz, nf, eig = mech.minimum(r0)
+    lp_o, nz_o, eig_o = MO.minimum(osys, otab, ids, fz, r0)
+    assert (nz, nf) == (nz_o, 0) and nz == 3
+    assert abs(lp - lp_o) < 1e-7 * abs(lp_o) and np.abs(eig - eig_o).max() < 1e-9
+    assert np.array_equal(mech.sep_list(r0), MO.sep_list(r0, ex))
+    # a saddle is not a minimum: the reference's verify fires (find.cpp:1120)
+    with pytest.raises(fly.OflyError, match="has eigenvalue"):
+        mech.minimum(sps[0])
+    mech.close()
+
+
+def test_every_saddle_prefactor_and_barrier_against_oracle(gpu, c3, capsys):
+    """Every saddle of the 64-search C3 batch: barrier 1e-6 eV, prefactor 1e-4 relative, same validity verdict."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    mech = fly.Mechanisms(data, fly.Box(tuple(ex)), ids, replicas=16)  # fewer slots than saddles: chunked
+    res = mech.prefactors(r0, sps)
+    lp_min, nz_min, _ = MO.minimum(osys, otab, ids, fz, r0)
+    osys.rebuild(otab.rcut, r0, 8)
+    e_min = osys.energy(ids, 8)
+    n_valid = 0
+    for k in range(len(sps)):
+        osys.rebuild(otab.rcut, sps[k], 8)
+        e_sp = osys.energy(ids, 8)
+        freq = MO.eigenvalues(osys.hessian(ids, fz, 8, mass_weight=True))
+        assert abs(res["barrier"][k] - (e_sp - e_min)) < 1e-6
+        assert abs(res["min_mode"][k] - freq[0]) < 1e-8
+        rest = freq[1:]
+        valid_o = freq[0] < -1e-6 and not (rest < -1e-6).any() and int((np.abs(rest) <= 1e-6).sum()) == nz_min
+        assert bool(res["valid"][k]) == bool(valid_o), (k, res["status"][k], freq[:6])
+        if valid_o:
+            nu_o = MO.prefactor(lp_min, float(np.log(rest[rest > 1e-6]).sum()))
+            assert abs(res["prefactor"][k] / nu_o - 1) < 1e-4
+            assert 1e11 < res["prefactor"][k] < 1e16
+            n_valid += 1
+    with capsys.disabled():
+        print(f"\n[prefactor parity] {n_valid}/{len(sps)} saddles valid first-order, all prefactors within 1e-4 of the oracle; "
+              f"statuses {sorted(set(res['status'].tolist()))}")
+    assert n_valid >= 15
+    mech.close()
+
+
+def test_saddle_to_mechanism_pathways_against_oracle(gpu, c3, capsys):
+    """do_adj_min + saddle_2_mech for the saddles of the batch at once vs the CPU composition one by one: same verdicts, pathway
+    end points to 1e-5 A, barrier / delta to 1e-6 eV, prefactor to 1e-4."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    S = min(len(sps), 12)
+    centre = len(ids) - 1
+    mech = fly.Mechanisms(data, fly.Box(tuple(ex)), ids, replicas=10)
+    lp, nz, nf, _ = mech.minimum(r0)
+    freeze = int(mech.sep_list(r0)[centre])
+    res = mech.from_saddles(r0, sps[:S], axs[:S], centre=centre, freeze_atom=freeze)
+    lp_o, nz_o, _ = MO.minimum(osys, otab, ids, fz, r0)
+    n_ok, verdicts = 0, []
+    for k in range(S):
+        o = MO.saddle_to_mech(osys, otab, ids, fz, r0, sps[k], axs[k], centre, freeze, nz_o)
+        verdicts.append((int(res["status"][k]), o["status"]))
+        assert res["status"][k] == o["status"], (k, verdicts)
+        if o["status"] in (1,):
+            continue
+        for name in ("rev", "sp", "fwd"):
+            assert np.abs(res[name][k] - o[name]).max() < 1e-5
+        if o["status"] == 2:
+            continue
+        for name in ("i2r", "r2f", "r2w", "w2f"):
+            assert abs(res[name][k] - o[name]) < 1e-5
+        if o["status"] == 0:
+            assert abs(res["barrier"][k] - o["barrier"]) < 1e-6 and abs(res["delta"][k] - o["delta"]) < 1e-6
+            assert abs(res["prefactor"][k] / MO.prefactor(lp_o, o["log_prod_eigen"]) - 1) < 1e-4
+            n_ok += 1
+    with capsys.disabled():
+        print(f"\n[mechanism parity] {n_ok}/{S} saddles became mechanisms on both sides; (gpu, oracle) verdicts {verdicts}")
+    assert n_ok >= 3
+    mech.close()
