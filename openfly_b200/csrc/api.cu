@@ -14,6 +14,7 @@
 #include "hessian.cuh"
 #include "internal.hpp"
 #include "neigh.cuh"
+#include "tile.cuh"
 
 namespace ofly {
 
@@ -112,12 +113,32 @@ namespace ofly {
     double vol = b->extents[0] * b->extents[1] * b->extents[2];
     double expect = (double)b->N / vol * (4.0 / 3.0) * M_PI * r_list * r_list * r_list;
     int K = (int)(1.4 * expect) + 16;
-    K = (K + 7) / 8 * 8;
+    K = (K + 15) / 16 * 16;  // rows are consumed in rounds of 16 entries (eam.cuh, VirtSum)
     if (K > b->d.K) {
       b->nbr.reserve(R * (size_t)b->N * K);
       b->d.K = K;
     }
     b->d.nbr = b->nbr.p;
+
+    // Cell-tiled fast path (tile.cuh): fully periodic boxes (every real atom then sits in a real cell, every image in the
+    // ghost layer) whose 4 x 4 x 4-cell windows fit the shared-memory budget.
+    TileDev &t = b->d.tile;
+    t = TileDev{};
+    const bool periodic = b->periodic[0] && b->periodic[1] && b->periodic[2];
+    if (periodic && env_int("OFLY_TILES", 0) && !b->tiles_off) {  // opt-in: measured slower than the row kernels (profiles/)
+      const double images = ratio * (double)b->N;
+      const double per_cell = images / (double)g.ncells;
+      long want = std::min<long>((long)(64 * per_cell * 1.35) + 64, (long)images + 64);
+      want = std::max<long>(want, b->tile_wcap);
+      if (want <= kTileMaxWindow) {
+        for (int i = 0; i < 3; i++) t.nt[i] = (g.shape[i] - 2 + 1) / 2;
+        t.n_tiles = t.nt[0] * t.nt[1] * t.nt[2];
+        t.wcap = (int)((want + 63) / 64 * 64);
+        b->tile_wcap = t.wcap;
+        b->nbr16.reserve(R * (size_t)b->N * b->d.K);
+        t.nbr16 = b->nbr16.p;
+      }
+    }
   }
 
   static void grow_after_fault(ofly_batch *b) {
@@ -131,6 +152,22 @@ namespace ofly {
     b->nbr.release();
     b->nbr.reserve(R * (size_t)b->N * K);
     b->d.K = K, b->d.nbr = b->nbr.p;
+    if (b->d.tile.n_tiles > 0) {  // the tile windows may have been what overflowed: more room, or back to the row kernels
+      if (b->d.tile.wcap >= kTileMaxWindow) {
+        b->tiles_off = true, b->d.tile = TileDev{};
+        b->nbr16.release();
+      } else {
+        b->d.tile.wcap = std::min(kTileMaxWindow, (b->d.tile.wcap * 3 / 2 + 63) / 64 * 64);
+        b->tile_wcap = b->d.tile.wcap;
+        b->nbr16.release();
+        b->nbr16.reserve(R * (size_t)b->N * K);
+        b->d.tile.nbr16 = b->nbr16.p;
+      }
+    }
+  }
+
+  static unsigned tile_grid(ofly_batch *b) {
+    return stride_grid(b->ctx, (size_t)b->R * (size_t)b->d.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12));
   }
 
   void enqueue_rebuild(ofly_batch *b, const double *pos_dev) {
@@ -143,6 +180,13 @@ namespace ofly {
     k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(b->d, all);
     k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(b->d, all);
     k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * b->d.grid.ncells + 127) / 128, 16), 128, 0, st>>>(b->d, all);
+    if (b->d.tile.n_tiles > 0) {
+      OFLY_CUDA(tile_prepare());
+      tile_launch_build(b->d, all, tile_grid(b), st);
+      ctx->launches += 5;
+      OFLY_CUDA(cudaGetLastError());
+      return;
+    }
     int G = env_int("OFLY_GROUP", 0);  // tuning override; the rows do not depend on the width
     if (!(G == 4 || G == 8 || G == 16 || G == 32)) G = build_group_for((long)atoms, (long)ctx->sm_count * 2048);
     const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), 8);
@@ -195,6 +239,13 @@ namespace ofly {
     TablesDev const &T = b->tables->dev;
     Sel all = all_replicas(b);
     const size_t stride = (size_t)3 * b->N;
+    if (b->d.tile.n_tiles > 0) {
+      OFLY_CUDA(tile_prepare());
+      tile_launch_gradient(b->d, T, all, tile_grid(b), st, grad_dev, stride, nullptr, 0);
+      ctx->launches += 2;
+      OFLY_CUDA(cudaGetLastError());
+      return;
+    }
     const int G = pick_group(ctx, (long)atoms);
     const unsigned gg = stride_grid(ctx, (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G)), env_int("OFLY_PAIR_CTAS", 32));
     switch (G) {
@@ -477,7 +528,7 @@ void ofly_batch_destroy(ofly_batch *b) {
   cudaStreamSynchronize(b->ctx->stream);
   if (b->sibling) ofly_batch_destroy(b->sibling), b->sibling = nullptr;
   b->search_graph.reset();
-  b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->cell_items.release();
+  b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->nbr16.release(), b->cell_items.release();
   b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release(), b->sel_all.release();
   b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();
   for (auto &buf : b->io_pool) buf.release();

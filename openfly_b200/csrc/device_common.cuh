@@ -50,6 +50,14 @@ namespace ofly {
     double r_cut, r_cut_sq;
   };
 
+  // Cell-tiled fast path (tile.cuh): tiles of 2 x 2 x 2 real cells; n_tiles == 0 switches it off.
+  struct TileDev {
+    int nt[3];        // tiles per axis
+    int n_tiles;
+    int wcap;         // window slots a CTA may stage (shared-memory budget)
+    uint16_t *nbr16;  // [R][N][K] neighbour entries as window slots, same rows as nbr
+  };
+
   struct BatchDev {
     int N, R, K;
     long img_cap;  // image slots per replica
@@ -66,6 +74,7 @@ namespace ofly {
     uint32_t *cell_items;   // [R][img_cap]     (j | code << 24) sorted inside each cell
     double4 *img_pos;       // [R][img_cap]     image position, w = bit pattern of the entry
     int *fault;             // [R]
+    TileDev tile;
   };
 
   // ---- 256-bit global loads (sm_100: LDG.E.256) ----------------------------------------------

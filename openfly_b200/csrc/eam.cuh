@@ -2,10 +2,12 @@
 // potential::EAM (src/potential/EAM/eam.cpp:33-120) iterating with neigh::List::for_neighbours
 // (include/libfly/neigh/list.hpp:138-154) and evaluating Spline::f/fp (spline.hpp:81-154).
 //
-// Two-pass, scatter-free gather. A sub-warp of G lanes owns one atom; lanes stride the atom's
-// neighbour row (coalesced 4 B entry loads), fetch each neighbour's {x,y,z,F'} record with one
-// 256-bit load, the spline knot {a,b,c,d} with one 256-bit read-only load, and the G partial sums
-// are combined with a fixed shuffle tree (deterministic order). No atomics, no stores to other atoms.
+// Two-pass, scatter-free gather. A sub-warp of G lanes owns one atom; each lane takes 16 / G consecutive
+// entries of every 16-entry round of the atom's neighbour row (one vector load), fetches each neighbour's
+// {x,y,z,F'} record with one 256-bit load, the spline knot {a,b,c,d} with one 256-bit read-only load, and the
+// partial sums are combined in a fixed, width-independent order (VirtSum). No atomics, no stores to other atoms.
+// These "row kernels" gather from global memory and work for every box; the tile kernels (tile.cuh) are the fast
+// path for fully periodic boxes and produce the same bits.
 //   pass 1: rho_b = sum_a phi_{a->b}(r);  F'_b = F_b'(rho_b) is stored in pos4[b].w   (eam.cpp:62-73)
 //   pass 2: grad_g = - sum_a [V'(r) + F'_g phi'_{a->g}(r) + F'_a phi'_{g->a}(r)] / r * dr (eam.cpp:90-107)
 // The FP64 pipe is the co-limiter of this path, so r and 1/r come from one rsqrt seed + one
@@ -16,6 +18,7 @@
 
 namespace ofly {
 
+  // One neighbour as the pair terms see it: image position minus centre, F'(rho) of the neighbour, its type.
   struct PairGeom {
     double dx, dy, dz;  // r_n - r_i, neighbour image minus centre (list.hpp:148)
     double r2;
@@ -23,28 +26,14 @@ namespace ofly {
     int j, tj;
   };
 
-  // Row entries are a pure stream (read once per pass, 0.4 GB per pass at C2): evict-first in L2 so that the 33 MB of
-  // position records and the 2.9 MB of tables, which every SM gathers from, stay resident.
-#ifndef OFLY_ROW_LOAD
-#define OFLY_ROW_LOAD 1
-#endif
-  __device__ __forceinline__ uint32_t ld_row(const uint32_t *p) {
-#if OFLY_ROW_LOAD == 0
-    return __ldg(p);
-#elif OFLY_ROW_LOAD == 1
-    uint32_t v;
-    asm("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-#else
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    uint32_t v;
-    asm("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-#endif
+  // Geometry of a pair from the neighbour's image position (already shifted) and the centre.
+  __device__ __forceinline__ void pair_geometry(PairGeom &g, double qx, double qy, double qz, const double4 &pi) {
+    g.dx = qx - pi.x, g.dy = qy - pi.y, g.dz = qz - pi.z;
+    g.r2 = fma(g.dz, g.dz, fma(g.dy, g.dy, g.dx * g.dx));
   }
 
-  // Decode one neighbour entry and fetch its record.
+  // Decode one neighbour entry and fetch its record from global memory. The image position is pos4[j] + shift, the
+  // arithmetic that created the reference's ghost atom; (x + 0.0) for the home image is x itself.
   __device__ __forceinline__ PairGeom load_pair(const BatchDev &B, const double4 *__restrict__ pos, const double4 &pi, uint32_t e) {
     PairGeom g;
     g.j = (int)(e & kIdxMask);
@@ -56,17 +45,7 @@ namespace ofly {
       int dxg = code % 3, dyg = (code / 3) % 3, dzg = code / 9;
       sx = shift_of(dxg, B.box.L[0]), sy = shift_of(dyg, B.box.L[1]), sz = shift_of(dzg, B.box.L[2]);
     }
-#ifdef OFLY_SHIFT_BRANCH
-    if (code == kShiftCentre) {  // most pairs: no image arithmetic ((x + 0.0) - y == x - y, same bits)
-      g.dx = pj.x - pi.x, g.dy = pj.y - pi.y, g.dz = pj.z - pi.z;
-    } else
-#endif
-    {
-      g.dx = (pj.x + sx) - pi.x;
-      g.dy = (pj.y + sy) - pi.y;
-      g.dz = (pj.z + sz) - pi.z;
-    }
-    g.r2 = fma(g.dz, g.dz, fma(g.dy, g.dy, g.dx * g.dx));
+    pair_geometry(g, pj.x + sx, pj.y + sy, pj.z + sz, pi);
     g.fprime_j = pj.w;
     return g;
   }
@@ -77,16 +56,6 @@ namespace ofly {
   // negative nor a NaN argument can index outside the table.
   __device__ __forceinline__ int knot_index(double x, double inv_dx, double dx, int n_knots, double &x0, bool &oob) {
     const double s = x * inv_dx;
-#ifdef OFLY_KNOT_INT
-    // the same test on the integer pipe (the FP64 pipe is the co-limiter): cvt.rzi saturates, so s <= -1 gives i < 0 and
-    // s >= n_knots gives i >= n_knots; NaN / Inf are caught by their exponent bits
-    int i = __double2int_rz(s);
-    if ((unsigned)i >= (unsigned)n_knots || (__double2hiint(s) & 0x7ff00000) == 0x7ff00000) {
-      oob = true;
-      i = i > 0 ? n_knots - 1 : 0;
-      if ((__double2hiint(s) & 0x7ff00000) == 0x7ff00000) i = 0;
-    }
-#else
     int i = 0;
     if (s > -1.0 && s < (double)n_knots) {
       i = __double2int_rz(s);
@@ -94,7 +63,6 @@ namespace ofly {
       oob = true;
       i = s > 0.0 ? n_knots - 1 : 0;  // NaN lands on 0
     }
-#endif
     x0 = fma(-(double)i, dx, x);
     return i;
   }
@@ -102,20 +70,49 @@ namespace ofly {
   __device__ __forceinline__ double spline_fp(const double4 &k, double x0) { return fma(x0, fma(x0 * 3.0, k.w, 2.0 * k.z), k.y); }
   __device__ __forceinline__ double spline_fpp(const double4 &k, double x0) { return fma(6.0 * x0, k.w, 2.0 * k.z); }
 
+  // ---- the pair terms, shared by the row kernels below and the tile kernels (tile.cuh): same bits on both paths ------
+  // pass 1 (eam.cpp:62-73, and :41-46 for the energy): rho += phi_{tj -> ti}(r) [, v += V(r)]
+  template <bool WITH_V>
+  __device__ __forceinline__ void rho_term(const TablesDev &T, int ti, const PairGeom &g, double &rho, double &v, bool &oob) {
+    if (g.r2 < T.r_cut_sq) {
+      double rr = g.r2 * fast_rsqrt(g.r2);
+      double x0;
+      int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
+      rho += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
+      if (WITH_V) {
+        int hi = max(ti, g.tj), lo = min(ti, g.tj);
+        v += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+      }
+    }
+  }
+  // pass 2 (eam.cpp:90-107): grad -= [V'(r) + F'_i phi'_{j->i}(r) + F'_j phi'_{i->j}(r)] / r * dr
+  __device__ __forceinline__ void force_term(const TablesDev &T, int ti, double Fi, const PairGeom &g, double &ax, double &ay, double &az, bool &oob) {
+    if (g.r2 < T.r_cut_sq) {
+      double rinv = fast_rsqrt(g.r2);
+      double rr = g.r2 * rinv;
+      double x0;
+      int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
+      int hi = max(ti, g.tj), lo = min(ti, g.tj);
+      double mag = spline_fp(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
+      double p_ji = spline_fp(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);  // phi(a -> g)
+      double p_ij = p_ji;
+      if (g.tj != ti) p_ij = spline_fp(ld256_nc(T.phi + (size_t)(ti + T.n_types * g.tj) * T.kR + idx), x0);  // phi(g -> a)
+      mag = fma(Fi, p_ji, mag);
+      mag = fma(g.fprime_j, p_ij, mag);
+      double s = mag * rinv;
+      ax = fma(-s, g.dx, ax), ay = fma(-s, g.dy, ay), az = fma(-s, g.dz, az);
+    }
+  }
+
   // ---- per-atom sums whose bits do not depend on the sub-warp width ---------------------------------
-  // Entry k of an atom's row belongs to *virtual lane* k % kVirt; a virtual lane adds its terms in ascending k, and the
-  // kVirt partial sums are combined by the butterfly (v, v^8), (v, v^4), (v, v^2), (v, v^1). A physical sub-warp of
-  // G <= kVirt lanes carries kVirt / G virtual lanes per thread (lane l owns v = l + G j, one accumulator each: the same
-  // entries k = l (mod G) a plain strided loop would give it), folds the upper butterfly levels in registers and does
-  // the remaining ones with shuffles. Every G therefore produces the SAME bits, so a replica's energies, forces and
-  // trajectory do not depend on how many replicas share its batch (the tick kernels pick G from the active count) or on
-  // how a batch is sharded over GPUs.
+  // A row is consumed in rounds of kVirt = 16 consecutive entries; entry k0 + v of a round belongs to *virtual lane* v, a
+  // virtual lane adds its terms in ascending k, and the 16 partial sums are combined by the butterfly (v, v^1), (v, v^2),
+  // (v, v^4), (v, v^8). A physical sub-warp of G lanes carries J = 16 / G consecutive virtual lanes per thread (lane l owns
+  // v = l J .. l J + J - 1: its entries of a round are contiguous, ONE vector load), folds the low butterfly levels in
+  // registers and does the remaining ones with shuffles. Every G therefore produces the SAME bits, and so does the tile
+  // path (tile.cuh), so a replica's energies, forces and trajectory do not depend on how many replicas share its batch
+  // (the tick kernels pick G from the active count), on the code path, or on how a batch is sharded over GPUs.
   constexpr int kVirt = 16;
-#ifdef OFLY_PLAIN_SUM  // tuning only: one accumulator per lane (the sums then depend on the sub-warp width)
-#define OFLY_VJ(j) 0
-#else
-#define OFLY_VJ(j) (j)
-#endif
 
   template <int G, int NS>
   struct VirtSum {
@@ -132,50 +129,61 @@ namespace ofly {
     // Totals on every lane of the sub-warp.
     __device__ __forceinline__ void total(double (&out)[NS]) {
 #pragma unroll
-      for (int h = J / 2; h >= 1; h >>= 1) {  // butterfly levels G*h = 8, 4 (those that stay inside a thread)
+      for (int h = 1; h < J; h <<= 1) {  // butterfly levels 1, 2 (those that stay inside a thread)
 #pragma unroll
-        for (int j = 0; j < h; j++) {
+        for (int j = 0; j < J; j += 2 * h) {
 #pragma unroll
           for (int q = 0; q < NS; q++) a[j][q] = a[j][q] + a[j + h][q];
         }
       }
+      const unsigned m = group_mask<G>();
 #pragma unroll
-      for (int q = 0; q < NS; q++) out[q] = group_sum<G>(a[0][q]);  // levels G/2 ... 1
+      for (int q = 0; q < NS; q++) {
+        double v = a[0][q];
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(m, v, o);  // levels J, 2 J, ... 8
+        out[q] = v;
+      }
     }
   };
+
+  // J consecutive row entries with one read-only vector load (rows are 64 B aligned, k is a multiple of J).
+  template <int J>
+  __device__ __forceinline__ void load_entries(const uint32_t *p, uint32_t (&e)[J]) {
+    if constexpr (J == 4) {
+      asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]) : "l"(p));
+    } else if constexpr (J == 2) {
+      asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(e[0]), "=r"(e[1]) : "l"(p));
+    } else {
+      asm("ld.global.nc.u32 %0, [%1];" : "=r"(e[0]) : "l"(p));
+    }
+  }
 
   // Pass 1 for atom i by a sub-warp of G lanes: returns rho_i on every lane. If WITH_V, also accumulates
   // sum_a V(r) (energy, eam.cpp:41-46) into *v_sum.
   template <int G, bool WITH_V>
   __device__ __forceinline__ double eam_rho_atom(const BatchDev &B, const TablesDev &T, int r, int i, int lane, double *v_sum, bool &oob) {
+    constexpr int J = kVirt / G;
     const double4 *pos = B.pos4 + (size_t)r * B.N;
     const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
     const int n = B.cnt[(size_t)r * B.N + i];
     const int ti = B.type[i];
     const double4 pi = ld256(pos + i);
-    VirtSum<G, WITH_V ? 2 : 1> acc;
-    for (int k0 = 0; k0 < n; k0 += kVirt) {
+    VirtSum<G, 2> acc;
+    for (int k0 = lane * J; k0 < n; k0 += kVirt) {
+      uint32_t e[J];
+      load_entries<J>(row + k0, e);
 #pragma unroll
-      for (int j = 0; j < kVirt / G; j++) {
-        const int k = k0 + lane + G * j;
-        if (k < n) {
-          PairGeom g = load_pair(B, pos, pi, ld_row(row + k));
-          if (g.r2 < T.r_cut_sq) {
-            double rr = g.r2 * fast_rsqrt(g.r2);
-            double x0;
-            int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
-            acc.a[OFLY_VJ(j)][0] += spline_f(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);
-            if (WITH_V) {
-              int hi = max(ti, g.tj), lo = min(ti, g.tj);
-              acc.a[OFLY_VJ(j)][1] += spline_f(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
-            }
-          }
+      for (int j = 0; j < J; j++) {
+        if (k0 + j < n) {
+          PairGeom g = load_pair(B, pos, pi, e[j]);
+          rho_term<WITH_V>(T, ti, g, acc.a[j][0], acc.a[j][1], oob);
         }
       }
     }
-    double tot[WITH_V ? 2 : 1];
+    double tot[2];
     acc.total(tot);
-    if (WITH_V) *v_sum = tot[WITH_V ? 1 : 0];
+    if (WITH_V) *v_sum = tot[1];
     return tot[0];
   }
 
@@ -183,6 +191,7 @@ namespace ofly {
   template <int G>
   __device__ __forceinline__ void eam_force_atom(const BatchDev &B, const TablesDev &T, int r, int i, int lane, double &gx, double &gy,
                                                  double &gz, bool &oob) {
+    constexpr int J = kVirt / G;
     const double4 *pos = B.pos4 + (size_t)r * B.N;
     const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
     const int n = B.cnt[(size_t)r * B.N + i];
@@ -190,28 +199,14 @@ namespace ofly {
     const double4 pi = ld256(pos + i);
     const double Fi = pi.w;
     VirtSum<G, 3> acc;
-    for (int k0 = 0; k0 < n; k0 += kVirt) {
+    for (int k0 = lane * J; k0 < n; k0 += kVirt) {
+      uint32_t e[J];
+      load_entries<J>(row + k0, e);
 #pragma unroll
-      for (int j = 0; j < kVirt / G; j++) {
-        const int k = k0 + lane + G * j;
-        if (k < n) {
-          PairGeom g = load_pair(B, pos, pi, ld_row(row + k));
-          if (g.r2 < T.r_cut_sq) {
-            double rinv = fast_rsqrt(g.r2);
-            double rr = g.r2 * rinv;
-            double x0;
-            int idx = knot_index(rr, T.inv_dR, T.dR, T.kR, x0, oob);
-            int hi = max(ti, g.tj), lo = min(ti, g.tj);
-            double mag = spline_fp(ld256_nc(T.V + (size_t)(hi + T.n_types * lo) * T.kR + idx), x0);
-            double p_ji = spline_fp(ld256_nc(T.phi + (size_t)(g.tj + T.n_types * ti) * T.kR + idx), x0);  // phi(a -> g)
-            double p_ij = p_ji;
-            if (g.tj != ti) p_ij = spline_fp(ld256_nc(T.phi + (size_t)(ti + T.n_types * g.tj) * T.kR + idx), x0);  // phi(g -> a)
-            mag = fma(Fi, p_ji, mag);
-            mag = fma(g.fprime_j, p_ij, mag);
-            double s = mag * rinv;
-            acc.a[OFLY_VJ(j)][0] = fma(-s, g.dx, acc.a[OFLY_VJ(j)][0]), acc.a[OFLY_VJ(j)][1] = fma(-s, g.dy, acc.a[OFLY_VJ(j)][1]),
-            acc.a[OFLY_VJ(j)][2] = fma(-s, g.dz, acc.a[OFLY_VJ(j)][2]);
-          }
+      for (int j = 0; j < J; j++) {
+        if (k0 + j < n) {
+          PairGeom g = load_pair(B, pos, pi, e[j]);
+          force_term(T, ti, Fi, g, acc.a[j][0], acc.a[j][1], acc.a[j][2], oob);
         }
       }
     }

@@ -98,12 +98,15 @@ struct ofly_batch {
   int periodic[3] = {1, 1, 1};
   double r_list = -1;  // radius the current grid was made for (-1: none yet)
   bool built = false;
+  bool tiles_off = false;  // the tile path overflowed its shared-memory budget once: row kernels from then on
+  int tile_wcap = 0;       // window budget reached so far (kept across grid changes)
   ofly::BatchDev d{};
   std::vector<uint8_t> type_host;
 
   ofly::DevBuf<uint8_t> type, frozen;
   ofly::DevBuf<double4> pos4, img_pos;
   ofly::DevBuf<uint32_t> nbr, cell_items;
+  ofly::DevBuf<uint16_t> nbr16;  // tile path (tile.cuh)
   ofly::DevBuf<int> cnt, cell_of, cell_count, cell_start, fault;
   ofly::DevBuf<int> sel_all;  // [R + 1]: 0..R-1 then R -- the "every replica" selection of the grid kernels
   ofly::DevBuf<double> stage_a, stage_b, stage_c, scratch;  // [R][3N] staging for the host-pointer entry points

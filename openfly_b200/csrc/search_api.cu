@@ -10,6 +10,7 @@
 
 #include "internal.hpp"
 #include "search.cuh"
+#include "tile.cuh"
 
 namespace ofly {
   // from api.cu
@@ -128,6 +129,7 @@ namespace ofly {
       OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_segment<C, MAXT>, B, P));
     }
 
+    ofly_ctx *ctx_of(ofly_batch *b) { return b->ctx; }
     unsigned stride_grid(ofly_ctx *ctx, size_t items, int per_sm) {
       return (unsigned)std::max<size_t>(1, std::min<size_t>(items, (size_t)ctx->sm_count * per_sm));
     }
@@ -185,6 +187,12 @@ namespace ofly {
       k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(B, reb);
       k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb);
       k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
+      if (B.tile.n_tiles > 0) {  // cell-tiled build (tile.cuh): same rows, candidates tested from shared memory
+        OFLY_CUDA(tile_prepare());
+        tile_launch_build(B, reb, stride_grid(ctx, (size_t)b->R * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st);
+        OFLY_CUDA(cudaGetLastError());
+        return;
+      }
       const PairGrid pg = pair_grid(b);
       switch (pg.forced) {
         case 16:
@@ -210,6 +218,13 @@ namespace ofly {
       Sel act{P.active, &P.ctl->n_active};
       const unsigned long long *goff = &P.state->gdst;
       const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
+      if (B.tile.n_tiles > 0) {  // cell-tiled passes (tile.cuh): same bits as the row kernels
+        OFLY_CUDA(tile_prepare());
+        tile_launch_gradient(B, T, act, stride_grid(ctx_of(b), (size_t)b->R * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st, P.ws,
+                             P.ws_stride, goff, goff_stride);
+        OFLY_CUDA(cudaGetLastError());
+        return;
+      }
       const PairGrid pg = pair_grid(b);
       switch (pg.forced) {
         case 16:
@@ -387,6 +402,7 @@ namespace ofly {
       double r_list = base_radius + skin;
       P.skin = skin;
       if (!(b->r_list == r_list)) make_grid_for(b, r_list);
+      if (b->d.tile.n_tiles > 0) OFLY_CUDA(tile_prepare());  // before any capture starts
 
       const size_t R = (size_t)b->R;
       const size_t n3p = ((size_t)3 * b->N + 3) & ~(size_t)3;

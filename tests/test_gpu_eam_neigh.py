@@ -291,3 +291,48 @@ def test_out_of_table_negative_density(gpu):
     nl.rebuild(pos)
     assert np.isfinite(fly.Generic(data).energy(nl)[0])
     s.close(), neg.close()
+
+
+def test_tile_path_equals_row_path(gpu):
+    """The cell-tiled kernels (tile.cuh: window staged in shared memory, 16-bit slot rows) against the row kernels
+    (OFLY_TILES=0): identical neighbour rows, and identical bits for energy and gradient -- on the C3-sized cell (3 real cells
+    per axis: partial tiles, windows that span almost the whole grid), a C1-sized cell and an odd, non-cubic box."""
+    import os
+
+    fly, ctx, data = gpu
+    cases = [bcc_vacancy(6, a=2.855, remove=(1,), jitter=0.05, hydrogen=True), bcc_vacancy(10, jitter=0.05, hydrogen=False)]
+    rng = np.random.default_rng(11)
+    ex = np.array([23.0, 17.5, 29.1])
+    cases.append((rng.random((1500, 3)) * ex * 0.999 + 0.5 * (rng.random((1500, 3)) - 0.5) * 0, ex, np.zeros(1500, np.uint32)))
+    for pos, ex, ids in cases:
+        if len(ids) == 1500:  # random gas: thin it so that no two atoms overlap (keeps rho inside the table)
+            keep = [0]
+            for k in range(1, len(pos)):
+                d = pos[keep] - pos[k]
+                d -= ex * np.round(d / ex)
+                if (d * d).sum(1).min() > 2.0 ** 2:
+                    keep.append(k)
+            pos, ids = pos[keep], ids[: len(keep)]
+        R = 2
+        P = np.stack([pos, pos + 0.02 * np.cos(np.arange(pos.size).reshape(pos.shape))])
+        out = {}
+        for mode in ("1", "0"):
+            os.environ["OFLY_TILES"] = mode
+            try:
+                s = fly.System(data, fly.Box(tuple(ex)), ids, replicas=R)
+                nl = fly.List(s, data.rcut() + 0.17)
+                nl.rebuild(P)
+                pot = fly.Generic(data)
+                d = 0.01 * np.sin(np.arange(P.size).reshape(P.shape))
+                g0 = pot.gradient(nl)
+                nl.update(d)
+                out[mode] = (nl.export(0), nl.export(1), pot.energy(nl), g0, pot.gradient(nl))
+                s.close()
+            finally:
+                del os.environ["OFLY_TILES"]
+        a, b = out["1"], out["0"]
+        for k in (0, 1):
+            for x, y in zip(a[k], b[k]):
+                assert np.array_equal(x, y)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+        assert np.abs(a[3]).max() > 1e-3

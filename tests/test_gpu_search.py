@@ -392,3 +392,21 @@ def test_search_graph_is_reused_between_calls(gpu, small_cell):
     for x, y, z in zip(a, b, c):
         assert np.array_equal(x, y) and np.array_equal(x, z)
     s.close()
+
+
+def test_search_on_tile_path_equals_row_path(gpu, small_cell):
+    """A whole batch of dimer searches with the cell-tiled kernels and with the row kernels (OFLY_TILES=0): same bits."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P, A = small_cell
+    pot = fly.Generic(data)
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["OFLY_TILES"] = mode
+        try:
+            s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
+            res[mode] = fly.Dimer().find_sp(s, P, A, r0, pot)
+            s.close()
+        finally:
+            del os.environ["OFLY_TILES"]
+    for x, y in zip(res["1"], res["0"]):
+        assert np.array_equal(x, y)
