@@ -525,7 +525,7 @@ def c3_environment(ctx, data, pot, dopt, ropt, seed):
     ok = np.nonzero(code == 0)[0]
     n_ok = len(ok)
     try:
-        mech = fly.Mechanisms(data, box, ids)
+        mech = fly.Mechanisms(data, box, ids, replicas=int(min(max(n_ok, 1), 192)))  # every saddle's Hessian in flight at once
         mech.prefactors(rmin[0], out_r[ok[:2]])  # warm-up
         t0 = time.perf_counter()
         res = mech.prefactors(rmin[0], out_r[ok])

@@ -11,6 +11,7 @@
 #include <sstream>
 
 #include "eam.cuh"
+#include "eigen.cuh"
 #include "hessian.cuh"
 #include "internal.hpp"
 #include "neigh.cuh"
@@ -764,10 +765,30 @@ namespace ofly {
   }
 
   // Hessian::eigenvalues() (hessian.hpp:86-93) of `count` dense symmetric n3 x n3 matrices on the device (lower triangle
-  // read, matrices destroyed), ascending, into eig_dev[count][n3]. The dense solve is cuSOLVER's Dsyevd (a library call;
-  // the own kernels of this path end at the assembled, mass-weighted matrix); the matrices of a batch are independent,
-  // so they are spread over a few solver lanes (handle + stream + workspace each) that run concurrently.
+  // read, matrices destroyed), ascending, into eig_dev[count][n3].
+  // Batches go to the own kernel (eigen.cuh: one CTA per matrix, all matrices in flight, HBM-bound); a few large matrices
+  // alone would leave most of the chip idle there and go to cuSOLVER's Dsyevd instead (a library call, loaded on first
+  // use; spread over a few solver lanes). OFLY_EIGEN=own / cusolver forces either.
   void eigenvalues_dev(ofly_ctx *ctx, double *H_dev, int n3, int count, double *eig_dev) {
+    char const *mode = std::getenv("OFLY_EIGEN");
+    const bool force_own = mode && std::string(mode) == "own", force_lib = mode && std::string(mode) == "cusolver";
+    if (n3 <= kEigMaxN && !force_lib && (force_own || count >= env_int("OFLY_EIGEN_MIN_BATCH", 6))) {
+      static unsigned long long allowed = 0;
+      const unsigned long long bit = 1ull << (ctx->device & 63);
+      if (!(allowed & bit)) {
+        OFLY_CUDA(cudaFuncSetAttribute(k_sym_eigenvalues, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem_bytes(kEigMaxN)));
+        allowed |= bit;
+      }
+      DevBuf<double> de;
+      de.reserve((size_t)count * 2 * (size_t)n3);
+      k_sym_eigenvalues<<<(unsigned)count, kEigThreads, eig_smem_bytes(n3), ctx->stream>>>(H_dev, (size_t)n3 * (size_t)n3, n3, eig_dev, de.p);
+      ctx->launches++;
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      de.release();
+      OFLY_CUDA(e);
+      return;
+    }
     Cusolver &cs = cusolver();
     if (!cs.ok()) throw Error(OFLY_ERR_CUDA, "libcusolver could not be loaded (needed for the dense symmetric eigenvalue solve)");
     const int lanes = std::max(1, std::min(std::min(count, env_int("OFLY_SOLVER_LANES", 4)), 16));
