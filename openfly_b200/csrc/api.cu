@@ -260,8 +260,8 @@ namespace ofly {
         break;
       default:
         k_eam_rho<4><<<gg, 256, 0, st>>>(b->d, T, all);
-        if (env_int("OFLY_FORCE_MINB", 4) == 3) {  // tuning: uncapped registers (80), three CTAs per SM
-          k_eam_force<4, 3><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
+        if (env_int("OFLY_FORCE_MINB", 3) == 4) {  // tuning: registers capped at 64 for four CTAs per SM
+          k_eam_force<4, 4><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
         } else {
           k_eam_force<4><<<gg, 256, 0, st>>>(b->d, T, all, grad_dev, stride, nullptr, 0);
         }

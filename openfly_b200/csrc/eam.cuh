@@ -276,8 +276,10 @@ namespace ofly {
       if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
   }
-  // MINB = CTAs per SM the register allocation is capped for (4: 64 registers, a few spilled bytes at G = 4; 3: 80).
-  template <int G, int MINB = 4>
+  // MINB = CTAs per SM the register allocation is capped for. 3 (80 registers, nothing spilled) is the default: capping at
+  // 64 registers for a fourth CTA spills ~100 bytes inside the pair loop (local-memory traffic on the L1 pipe that
+  // already bounds the kernel): measured 0.857 ms against 0.819 per launch pair, 620 against 569 ms per 64-search step.
+  template <int G, int MINB = 3>
   static __global__ void __launch_bounds__(256, MINB) k_eam_force(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
                                                             const unsigned long long *__restrict__ offset, size_t offset_stride) {
     eam_force_tiles<G>(B, T, S, out, stride, offset, offset_stride);
@@ -316,7 +318,10 @@ namespace ofly {
     }
     kernel_stamp(trace, trace_cap, 92);
   }
-  static __global__ void __launch_bounds__(256, 4) k_eam_force_dyn(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
+#ifndef OFLY_DYN_MINB
+#define OFLY_DYN_MINB 3
+#endif
+  static __global__ void __launch_bounds__(256, OFLY_DYN_MINB) k_eam_force_dyn(BatchDev B, TablesDev T, Sel S, double *__restrict__ out, size_t stride,
                                                                 const unsigned long long *__restrict__ offset, size_t offset_stride, long slots,
                                                                 unsigned long long *trace, int trace_cap) {
     kernel_stamp(trace, trace_cap, 93);
