@@ -47,7 +47,7 @@ C5_TOTAL, C5_SLOTS = 2048, 1024
 METRIC, UNIT = "eam_atom_gradient_evals_per_s", "atom-evals/s"
 WORKLOAD = ("C2: bcc Fe 20^3 (a=2.8553) - 1 vacancy + 1 H = 16000 atoms, Wen Fe-H EAM, dimer searches (Dimer::find_sp, default options) "
             "from Master::perturb start states: 64 concurrent searches per GPU, 256 queued per GPU and step")
-CPU_SAMPLE_MAX_STEPS = 12  # translation steps per CPU search in the bounded sample
+CPU_SAMPLE_MAX_STEPS = 40  # translation steps per CPU search in the bounded sample (a full search averages ~45; shorter cuts flatter the CPU: the first steps rarely rebuild the list)
 
 
 def config_dict(seed: int):

@@ -197,8 +197,10 @@ namespace ofly {
     int n = B.grid.ncells;
     int per = (n + blockDim.x - 1) / blockDim.x;
     int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    // The histogram is produced by atomics (performed in L2); read it there: a CTA that runs several rebuilds in one
+    // kernel (the resident engine, search.cuh) may still hold an older copy of these lines in its L1.
     int sum = 0;
-    for (int c = lo; c < hi; c++) sum += hist[c];
+    for (int c = lo; c < hi; c++) sum += __ldcg(hist + c);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int inc = sum;
 #pragma unroll
@@ -223,7 +225,7 @@ namespace ofly {
     int run = sm[w] + inc - sum;
     for (int c = lo; c < hi; c++) {
       start[c] = run;
-      run += hist[c];
+      run += __ldcg(hist + c);
     }
     if (threadIdx.x == 0) {
       start[n] = sm[32];
