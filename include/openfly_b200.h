@@ -122,6 +122,12 @@ int ofly_neigh_positions(ofly_batch *b, long replica, double *pos_host);
 /* Mean stored neighbours per atom over the whole batch (for the roofline's n-bar). */
 int ofly_neigh_mean_count(ofly_batch *b, double *mean);
 
+/* List::for_neighbours (list.hpp:138-154) of ONE atom, evaluated on the device: the neighbours of `atom` within r_cut as
+ * (real index, r, dr = r_n - r_i with the image shift applied), in stored order; only the hits travel. idx: [cap], r: [cap],
+ * dr: [cap][3]; *count receives the number of hits (may exceed cap). For iterating over ALL atoms use ofly_neigh_export once. */
+int ofly_neigh_for_atom(ofly_batch *b, long replica, long atom, double r_cut, int *idx_host, double *r_host, double *dr_host, long cap,
+                        long *count);
+
 /* ---- potential::Generic (EAM) over the batch's current list ---------------------------------- */
 
 /* energy (eam.cpp:33-51): out [R]. */
@@ -279,6 +285,18 @@ int ofly_mech_minimum(ofly_batch *b, const double *in_min_host, double zero_tol,
 int ofly_mech_from_saddles(ofly_batch *b, const ofly_mech_options *opt, const ofly_lbfgs_options *min_opt, long n_saddles,
                            const double *sp_host, const double *axis_host, const double *in_min_host, double *rev_host,
                            double *sp_out_host, double *fwd_host, ofly_mech_record *records);
+/* Master::perturb (find.cpp:1147-1214) for n_states start states at once. The batch's list is rebuilt from in_min at r_pert
+ * (nl_pert, find.cpp:217-219). The caller draws the random numbers (the reference draws from a thread-local Xoshiro in
+ * list order, which has no meaning here): stddev: [n] (the accepted N(stddev, stddev/3) draws), normals: [n][N][6] standard
+ * normal draws per atom -- three for the displacement (scaled by stddev (1 - r / r_pert)), three for the axis; only atoms
+ * within r_pert of `centre` use theirs. pos_out / axis_out: [n][3N]; axes are normalised. */
+int ofly_master_perturb(ofly_batch *b, long n_states, const double *in_min_host, long centre, double r_pert, const double *stddev_host,
+                        const double *normals_host, double *pos_out_host, double *axis_out_host);
+/* The numeric part of one SKMC step (include/libfly/kinetic/skmc.hpp:297-309): E0 = energy(cell); relax the reconstructed
+ * state; centroid_align(rel_recon, raw_recon); Ef = energy(rel_recon); dR = |rel_recon - raw_recon|. One call, every
+ * intermediate on the device. rel_recon: [3N] or NULL. *min_failed follows LBFGS::minimise's bool. */
+int ofly_skmc_relax_step(ofly_batch *b, const ofly_lbfgs_options *min_opt, const double *cell_host, const double *raw_recon_host,
+                         double *rel_recon_host, double *E0, double *Ef, double *dR, int *min_failed);
 /* find.cpp:287: sqrt(exp(log_prod_eigen_min - log_prod_eigen_sp) / (2 pi 1.6605390666050e-27)), in Hz. */
 double ofly_mech_prefactor(double log_prod_eigen_min, double log_prod_eigen_sp);
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "internal.hpp"
+#include "neigh.cuh"
 
 namespace ofly {
   // api.cu (the first three are defined inside its extern "C" block)
@@ -201,6 +202,113 @@ namespace ofly {
       }
     }
 
+    // List::for_neighbours (list.hpp:138-154) of ONE atom, served on the device: entries of atom i's row within r_cut as
+    // (real index, r, dr) triples, compacted in row order. One warp.
+    __global__ void __launch_bounds__(32) k_neigh_for_atom(BatchDev B, int r, int i, double r_cut_sq, int cap, int *__restrict__ idx,
+                                                           double *__restrict__ dist, double *__restrict__ dr, int *__restrict__ count) {
+      const double4 *pos = B.pos4 + (size_t)r * B.N;
+      const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
+      const int n = B.cnt[(size_t)r * B.N + i];
+      const double4 pi = pos[i];
+      int found = 0;
+      for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + (int)threadIdx.x;
+        bool hit = false;
+        int j = 0;
+        double dx = 0, dy = 0, dz = 0, r2 = 0;
+        if (k < n) {
+          const uint32_t e = row[k];
+          j = (int)(e & kIdxMask);
+          const int code = (int)((e >> 24) & 31u);
+          const double4 pj = pos[j];
+          dx = (pj.x + shift_of(code % 3, B.box.L[0])) - pi.x;
+          dy = (pj.y + shift_of((code / 3) % 3, B.box.L[1])) - pi.y;
+          dz = (pj.z + shift_of(code / 9, B.box.L[2])) - pi.z;
+          r2 = (dx * dx + dy * dy) + dz * dz;  // gnorm_sq's order (core.hpp:655-680)
+          hit = r2 < r_cut_sq;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int w = found + __popc(bal & ((1u << threadIdx.x) - 1u));
+          if (w < cap) idx[w] = j, dist[w] = sqrt(r2), dr[3 * w] = dx, dr[3 * w + 1] = dy, dr[3 * w + 2] = dz;
+        }
+        found += __popc(bal);
+      }
+      if (threadIdx.x == 0) *count = found;
+    }
+
+    // Master::perturb (find.cpp:1147-1214) for one start state per CTA. z: this state's standard normal draws, [N][6]
+    // (three for the position, three for the axis of every atom; only those of atoms inside r_pert are used).
+    __global__ void __launch_bounds__(kMechThreads) k_master_perturb(BatchDev B, int centre, double r_pert, const double *__restrict__ in_min,
+                                                                     const double *__restrict__ stddev, const double *__restrict__ z_all,
+                                                                     double *__restrict__ pos_out, double *__restrict__ axis_out) {
+      __shared__ double sm[8];
+      const size_t s = blockIdx.x;
+      const int n3 = 3 * B.N;
+      double *out = pos_out + s * n3, *ax = axis_out + s * n3;
+      const double *z = z_all + s * (size_t)B.N * 6;
+      const double sd = stddev[s];
+      for (int t = threadIdx.x; t < n3; t += kMechThreads) out[t] = in_min[t], ax[t] = 0.0;
+      __syncthreads();
+      // neighbours of the centre within r_pert, from replica 0's list (built from in_min at a radius >= r_pert)
+      const double4 *pos = B.pos4;
+      const uint32_t *row = B.nbr + (size_t)centre * B.K;
+      const int n = B.cnt[centre];
+      const double4 pc = pos[centre];
+      for (int k = threadIdx.x; k < n; k += kMechThreads) {
+        const uint32_t e = row[k];
+        const int j = (int)(e & kIdxMask), code = (int)((e >> 24) & 31u);
+        const double4 pj = pos[j];
+        const double dx = (pj.x + shift_of(code % 3, B.box.L[0])) - pc.x, dy = (pj.y + shift_of((code / 3) % 3, B.box.L[1])) - pc.y,
+                     dz = (pj.z + shift_of(code / 9, B.box.L[2])) - pc.z;
+        const double r2 = (dx * dx + dy * dy) + dz * dz;
+        if (r2 < r_pert * r_pert && !B.frozen[j]) {
+          const double env = 1. - sqrt(r2) / r_pert;
+          for (int c = 0; c < 3; c++) {  // atomics: the same atom may be reached through two images in a small box
+            atomicAdd(out + 3 * j + c, sd * z[6 * j + c] * env);
+            atomicAdd(ax + 3 * j + c, z[6 * j + 3 + c]);
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        out[3 * centre + threadIdx.x] += sd * z[6 * centre + threadIdx.x];
+        ax[3 * centre + threadIdx.x] += z[6 * centre + 3 + threadIdx.x];
+      }
+      __syncthreads();
+      double a[1] = {0};
+      for (int t = threadIdx.x; t < n3; t += kMechThreads) a[0] = fma(ax[t], ax[t], a[0]);
+      block_sum<1>(a, sm);
+      const double nrm = sqrt(a[0]);
+      for (int t = threadIdx.x; t < n3; t += kMechThreads) ax[t] /= nrm;
+    }
+
+    // centroid_align(x, with) (lattice.hpp:214-226) followed by gnorm(x - with): one CTA.
+    __global__ void __launch_bounds__(kMechThreads) k_centroid_align(int N, double *__restrict__ x, const double *__restrict__ with, double *__restrict__ norm_out) {
+      __shared__ double sm[6 * 8];
+      double c[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = threadIdx.x; i < N; i += kMechThreads) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) c[k] += with[3 * i + k], c[3 + k] += x[3 * i + k];
+      }
+      block_sum<6>(c, sm);
+      double delta[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) delta[k] = c[k] / (double)N - c[3 + k] / (double)N;
+      double a[1] = {0};
+      for (int i = threadIdx.x; i < N; i += kMechThreads) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double v = x[3 * i + k] + delta[k];
+          x[3 * i + k] = v;
+          const double d = v - with[3 * i + k];
+          a[0] = fma(d, d, a[0]);
+        }
+      }
+      block_sum<1>(a, sm);
+      if (threadIdx.x == 0) *norm_out = sqrt(a[0]);
+    }
+
     // Eigenvalue rules shared by the minimum and the saddles (find.cpp:849-864, 1118-1128): modes [first, n) are summed if
     // > tol, counted as zero if within tol; a mode < -tol stops the scan. Returns the index of that mode or -1.
     int scan_modes(const double *freq, int n, int first, double tol, double &log_sum, int &zeros) {
@@ -286,6 +394,112 @@ int ofly_mech_sep_list(ofly_batch *b, const double *pos_host, int *sep_host) {
     OFLY_CUDA(cudaMemcpyAsync(sep_host, out.p, sizeof(int) * (size_t)b->N, cudaMemcpyDeviceToHost, st));
     OFLY_CUDA(cudaStreamSynchronize(st));
     out.release();
+  });
+}
+
+int ofly_neigh_for_atom(ofly_batch *b, long replica, long atom, double r_cut, int *idx_host, double *r_host, double *dr_host, long cap,
+                        long *count) {
+  return guarded([&] {
+    require(b && idx_host && r_host && dr_host && count && cap >= 0, "null argument");
+    require(b->built, "for_neighbours before rebuild()");
+    require(replica >= 0 && replica < b->R && atom >= 0 && atom < b->N, "Atom is not in neighbour list");
+    require(r_cut <= b->r_list, "r_cut is bigger then than the internal r_cut");  // list.hpp:141-143
+    OFLY_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const size_t K = (size_t)b->d.K;
+    DevBuf<int> d_idx;
+    DevBuf<double> d_val;
+    d_idx.reserve(K + 1), d_val.reserve(4 * K);
+    k_neigh_for_atom<<<1, 32, 0, st>>>(b->d, (int)replica, (int)atom, r_cut * r_cut, (int)K, d_idx.p + 1, d_val.p, d_val.p + K, d_idx.p);
+    b->ctx->launches++;
+    std::vector<int> hi(K + 1);
+    std::vector<double> hv(4 * K);
+    OFLY_CUDA(cudaMemcpyAsync(hi.data(), d_idx.p, (K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaMemcpyAsync(hv.data(), d_val.p, 4 * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    d_idx.release(), d_val.release();
+    OFLY_CUDA(e);
+    const long n = hi[0];
+    *count = n;
+    for (long k = 0; k < std::min(n, cap); k++) {
+      idx_host[k] = hi[(size_t)k + 1], r_host[k] = hv[(size_t)k];
+      for (int c = 0; c < 3; c++) dr_host[3 * k + c] = hv[K + 3 * (size_t)k + c];
+    }
+  });
+}
+
+int ofly_master_perturb(ofly_batch *b, long n_states, const double *in_min_host, long centre, double r_pert, const double *stddev_host,
+                        const double *normals_host, double *pos_out_host, double *axis_out_host) {
+  return guarded([&] {
+    require(b && in_min_host && stddev_host && normals_host && pos_out_host && axis_out_host, "null argument");
+    require(n_states >= 1 && centre >= 0 && centre < b->N, "bad argument");
+    require(!b->frozen_host[(size_t)centre], "perturbation centred on a frozen atom");  // find.cpp:1205
+    OFLY_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const size_t n3 = 3 * (size_t)b->N, S = (size_t)n_states;
+    // nl_pert (find.cpp:217-219): replica 0's list rebuilt from the minimum at r_pert
+    b->stage_a.reserve((size_t)b->R * n3);
+    for (long r = 0; r < b->R; r++) OFLY_CUDA(cudaMemcpyAsync(b->stage_a.p + (size_t)r * n3, in_min_host, n3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rebuild_checked(b, r_pert, b->stage_a.p);
+    DevBuf<double> d_sd, d_z, d_pos, d_ax;
+    struct Rel {
+      DevBuf<double> *v[4];
+      ~Rel() {
+        for (auto *x : v) x->release();
+      }
+    } rel{{&d_sd, &d_z, &d_pos, &d_ax}};
+    d_sd.reserve(S), d_z.reserve(S * 6 * (size_t)b->N), d_pos.reserve(S * n3), d_ax.reserve(S * n3);
+    OFLY_CUDA(cudaMemcpyAsync(d_sd.p, stddev_host, S * sizeof(double), cudaMemcpyHostToDevice, st));
+    OFLY_CUDA(cudaMemcpyAsync(d_z.p, normals_host, S * 6 * (size_t)b->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_master_perturb<<<(unsigned)S, kMechThreads, 0, st>>>(b->d, (int)centre, r_pert, b->stage_a.p, d_sd.p, d_z.p, d_pos.p, d_ax.p);
+    OFLY_CUDA(cudaGetLastError());
+    b->ctx->launches++;
+    OFLY_CUDA(cudaMemcpyAsync(pos_out_host, d_pos.p, S * n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaMemcpyAsync(axis_out_host, d_ax.p, S * n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int ofly_skmc_relax_step(ofly_batch *b, const ofly_lbfgs_options *min_opt, const double *cell_host, const double *raw_recon_host,
+                         double *rel_recon_host, double *E0, double *Ef, double *dR, int *min_failed) {
+  return guarded([&] {
+    require(b && min_opt && cell_host && raw_recon_host && E0 && Ef && dR && min_failed, "null argument");
+    OFLY_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const size_t n3 = 3 * (size_t)b->N;
+    DevBuf<double> d_cell, d_raw, d_rel, d_norm;
+    DevBuf<int> d_status;
+    struct Rel {
+      DevBuf<double> *v[4];
+      DevBuf<int> *i;
+      ~Rel() {
+        for (auto *x : v) x->release();
+        i->release();
+      }
+    } rel{{&d_cell, &d_raw, &d_rel, &d_norm}, &d_status};
+    d_cell.reserve(n3), d_raw.reserve(n3), d_rel.reserve(n3), d_norm.reserve(1), d_status.reserve(1);
+    OFLY_CUDA(cudaMemcpyAsync(d_cell.p, cell_host, n3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    OFLY_CUDA(cudaMemcpyAsync(d_raw.p, raw_recon_host, n3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<double> e;
+    std::vector<int> fault;
+    energies_of(b, {d_cell.p}, e, fault);  // E0 = energy(cell), skmc.hpp:297
+    if (fault[0] & kFaultOutOfBounds) throw Error(OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region (Spline::OutOfBounds)");
+    *E0 = e[0];
+    int rc = ofly_lbfgs_minimise_stream_dev(b, min_opt, 1, d_raw.p, d_rel.p, nullptr, d_status.p, nullptr);  // skmc.hpp:301-303
+    if (rc != OFLY_OK) throw Error(rc, ofly_last_error());
+    int status = 0;
+    OFLY_CUDA(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    k_centroid_align<<<1, kMechThreads, 0, st>>>((int)b->N, d_rel.p, d_raw.p, d_norm.p);  // skmc.hpp:305, 309
+    OFLY_CUDA(cudaGetLastError());
+    b->ctx->launches++;
+    OFLY_CUDA(cudaMemcpyAsync(dR, d_norm.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (rel_recon_host) OFLY_CUDA(cudaMemcpyAsync(rel_recon_host, d_rel.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaStreamSynchronize(st));
+    if (status == -5) throw Error(OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region (Spline::OutOfBounds)");
+    *min_failed = status != 0;
+    energies_of(b, {d_rel.p}, e, fault);  // Ef = energy(rel_recon), skmc.hpp:307
+    if (fault[0] & kFaultOutOfBounds) throw Error(OFLY_ERR_OUT_OF_BOUNDS, "x is outside tabulated region (Spline::OutOfBounds)");
+    *Ef = e[0];
   });
 }
 

@@ -224,20 +224,24 @@ class List:
         return m.value
 
     def for_neighbours(self, i: int, r_cut: float, f, replica: int = 0) -> None:
-        """Call f(n, r, dr) for every neighbour of atom i within r_cut (list.hpp:138-154)."""
+        """Call f(n, r, dr) for every neighbour of atom i within r_cut (list.hpp:138-154). Evaluated on the device for this
+        one atom (ofly_neigh_for_atom): only the hits travel."""
         if r_cut > self.r_cut:
             raise OflyError(capi.OFLY_ERR_INVALID, f"r_cut={r_cut} is bigger then than the internal r_cut={self.r_cut}")
-        counts, idx, sh = self.export(replica)
-        pos = self.positions(replica)
-        L = np.asarray(self.sys.box.extents)
-        off = int(counts[:i].sum())
-        for k in range(off, off + int(counts[i])):
-            code = int(sh[k])
-            s = np.array([code % 3 - 1, (code // 3) % 3 - 1, code // 9 - 1], dtype=np.float64)
-            dr = (pos[idx[k]] + s * L) - pos[i]
-            r_sq = (dr[0] * dr[0] + dr[1] * dr[1]) + dr[2] * dr[2]
-            if r_sq < r_cut * r_cut:
-                f(int(idx[k]), float(np.sqrt(r_sq)), dr)
+        idx, r, dr = self.neighbours_of(i, r_cut, replica)
+        for k in range(len(idx)):
+            f(int(idx[k]), float(r[k]), dr[k])
+
+    def neighbours_of(self, i: int, r_cut: float, replica: int = 0):
+        """(real index[n], r[n], dr[n, 3]) of atom i's neighbours within r_cut, in stored order."""
+        cap = 1024
+        idx = np.zeros(cap, dtype=np.int32)
+        r = np.zeros(cap)
+        dr = np.zeros((cap, 3))
+        n = C.c_long()
+        check(self.sys.ctx.lib.ofly_neigh_for_atom(self.sys.h, replica, i, r_cut, ptr(idx, _ip), ptr(r, _dp), ptr(dr, _dp), cap, C.byref(n)))
+        assert n.value <= cap
+        return idx[:n.value].copy(), r[:n.value].copy(), dr[:n.value].copy()
 
 
 class Generic:
@@ -390,6 +394,29 @@ class Mechanisms:
 
     def close(self) -> None:
         self.sys.close()
+
+    def perturb(self, in_min, centre: int, stddev, normals, r_pert: float = 4.0):
+        """Master::perturb (find.cpp:1147-1214) for S start states: stddev [S], normals [S, N, 6] (the caller's random draws).
+        Returns (positions [S, N, 3], unit axes [S, N, 3])."""
+        N = self.sys.N
+        mn = f64(in_min).reshape(N, 3)
+        sd = f64(stddev).reshape(-1)
+        z = f64(normals).reshape(len(sd), N, 6)
+        pos = np.zeros((len(sd), N, 3))
+        ax = np.zeros_like(pos)
+        check(self.lib.ofly_master_perturb(self.sys.h, len(sd), ptr(mn, _dp), centre, r_pert, ptr(sd, _dp), ptr(z, _dp), ptr(pos, _dp), ptr(ax, _dp)))
+        return pos, ax
+
+    def skmc_relax_step(self, cell, raw_recon, min_opt: LbfgsOptions | None = None):
+        """The numeric part of one SKMC step (skmc.hpp:297-309): returns dict(E0, Ef, dR, failed, rel_recon)."""
+        N = self.sys.N
+        a, b = f64(cell).reshape(N, 3), f64(raw_recon).reshape(N, 3)
+        rel = np.zeros((N, 3))
+        e0, ef, dr, failed = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        o = min_opt or lbfgs_options()
+        check(self.lib.ofly_skmc_relax_step(self.sys.h, C.byref(o), ptr(a, _dp), ptr(b, _dp), ptr(rel, _dp), C.byref(e0), C.byref(ef), C.byref(dr),
+                                            C.byref(failed)))
+        return {"E0": e0.value, "Ef": ef.value, "dR": dr.value, "failed": bool(failed.value), "rel_recon": rel}
 
     def sep_list(self, positions) -> np.ndarray:
         p = f64(positions).reshape(self.sys.N, 3)

@@ -191,3 +191,75 @@ def test_own_eigenvalue_kernel_against_cusolver_and_numpy(gpu, c3, oracle_lib):
     assert np.abs(many["min_mode"] - lib["min_mode"]).max() < 1e-9
     ok = many["status"] == 0
     assert np.abs(many["log_prod_eigen"][ok] - lib["log_prod_eigen"][ok]).max() < 1e-7
+
+
+def test_for_neighbours_of_one_atom_on_device(gpu, c3):
+    """ofly_neigh_for_atom against the oracle's List::for_neighbours (list.hpp:138-154): same neighbours, r and dr."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, 4.0 + 0.3)
+    nl.rebuild(sps[0])
+    osys.rebuild(4.3, sps[0])
+    for atom in (0, 17, len(ids) - 1):
+        for r_cut in (4.0, 2.6):
+            idx, r, dr = nl.neighbours_of(atom, r_cut)
+            o_idx, o_r, o_dr = osys.for_neighbours(atom, r_cut)
+            a, b = np.lexsort((r, idx)), np.lexsort((o_r, o_idx))
+            assert np.array_equal(idx[a], np.asarray(o_idx)[b])
+            assert np.abs(r[a] - np.asarray(o_r)[b]).max() < 1e-12 and np.abs(dr[a] - np.asarray(o_dr)[b]).max() < 1e-12
+    seen = []
+    nl.for_neighbours(5, 3.0, lambda n, r, dr: seen.append((n, r)))
+    assert len(seen) == len(osys.for_neighbours(5, 3.0)[0])
+    with pytest.raises(fly.OflyError):
+        nl.neighbours_of(0, 5.0)  # beyond the list radius (list.hpp:141-143)
+    s.close()
+
+
+def test_master_perturb_on_device(gpu, c3):
+    """Master::perturb (find.cpp:1147-1214) with the caller's normal draws against a numpy restatement: atoms within r_pert of
+    the centre get stddev * z * (1 - r / r_pert) and an axis component, the centre a full kick, the axis is normalised."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    N, centre, r_pert = len(ids), len(ids) - 1, 4.0
+    rng = np.random.default_rng(3)
+    S = 5
+    sd = np.abs(rng.normal(0.6, 0.2, S))
+    z = rng.normal(size=(S, N, 6))
+    mech = fly.Mechanisms(data, fly.Box(tuple(ex)), ids, replicas=2)
+    pos, ax = mech.perturb(r0, centre, sd, z, r_pert)
+    mech.close()
+    osys.rebuild(r_pert, r0)
+    o_idx, o_r, _ = osys.for_neighbours(centre, r_pert)
+    for s in range(S):
+        want_p, want_a = r0.copy(), np.zeros_like(r0)
+        for n, r in zip(o_idx, o_r):
+            want_p[n] += sd[s] * z[s, n, :3] * (1 - r / r_pert)
+            want_a[n] += z[s, n, 3:]
+        want_p[centre] += sd[s] * z[s, centre, :3]
+        want_a[centre] += z[s, centre, 3:]
+        want_a /= np.sqrt((want_a ** 2).sum())
+        assert np.abs(pos[s] - want_p).max() < 1e-12 and np.abs(ax[s] - want_a).max() < 1e-12
+        assert abs((ax[s] ** 2).sum() - 1) < 1e-12
+        moved = np.nonzero(np.abs(pos[s] - r0).max(axis=1) > 0)[0]
+        assert set(moved.tolist()) == set(int(n) for n in o_idx) | {centre}
+
+
+def test_skmc_relax_step(gpu, c3, oracle_lib):
+    """skmc.hpp:297-309 in one call against the CPU composition: E0, relaxed state, aligned displacement, Ef."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    raw = oracle_lib.jitter(r0, (7, 7, 7, 7), 0.03)
+    mech = fly.Mechanisms(data, fly.Box(tuple(ex)), ids, replicas=1)
+    got = mech.skmc_relax_step(r0, raw)
+    mech.close()
+    rel, _, failed, _ = osys.minimise(raw, ids, fz, threads=8)
+    rel = rel + (raw.mean(axis=0) - rel.mean(axis=0))
+    osys.rebuild(otab.rcut, r0)
+    e0 = osys.energy(ids)
+    osys.rebuild(otab.rcut, rel)
+    ef = osys.energy(ids)
+    assert got["failed"] == bool(failed)
+    assert abs(got["E0"] - e0) < 1e-9 and abs(got["Ef"] - ef) < 1e-8
+    assert np.abs(got["rel_recon"] - rel).max() < 1e-6
+    assert abs(got["dR"] - np.sqrt(((rel - raw) ** 2).sum())) < 1e-5
