@@ -429,10 +429,14 @@ namespace ofly {
       const long rounds = (n_queue + n0 - 1) / n0;  // searches a slot may run one after the other
       P.max_ticks = (int)std::min<long>(((long)(P.iter_max + 1) * per_step + 8) * rounds, 1L << 30);
 
-      // OFLY_LBFGS=twoloop selects the pass-per-pair recursion (A/B comparisons); default is the single-pass step.
+      // The L-BFGS step is the literal two-loop recursion of lbfgs_core.cpp:29-87 (one pass per history pair). OFLY_LBFGS=gram
+      // selects the two-pass Gram form (newton_step_gram): 5-10 % faster per step, but its alpha / beta come out of differences
+      // of large dot products and are rounded ~1e-12 apart from the recursion's -- on 256 searches against the CPU oracle
+      // 5 trajectories branch to another saddle with it (the earliest after 317 evaluations) against 2 (after 1336) with the
+      // literal order (scripts/lbfgs_branch_study.py), so the reference's arithmetic is the default.
       P.gram = [] {
         char const *v = std::getenv("OFLY_LBFGS");
-        return !(v && std::string(v) == "twoloop");
+        return (v && std::string(v) == "gram") ? 1 : 0;
       }();
       const bool device_loop = [] {
         char const *v = std::getenv("OFLY_SEARCH_LOOP");

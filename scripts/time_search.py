@@ -12,7 +12,7 @@ pot = fly.Generic(data)
 pos, ex, ids = inputs.iron_hydrogen_cell(n, 2.855, remove=(1,), hydrogen=True)
 s1 = fly.System(data, fly.Box(tuple(ex)), ids)
 t0 = time.perf_counter(); rmin, _, failed, c1 = fly.LBFGS().minimise(s1, pos, pot); t1 = time.perf_counter() - t0
-print(f"[{os.environ.get('OFLY_LBFGS', 'gram')} if={os.environ.get('OFLY_REBUILD_IF', '1')}] minimise N={len(ids)}: {t1*1e3:.1f} ms, evals {c1[0,0]}, {t1/c1[0,0]*1e6:.1f} us/tick")
+print(f"[{os.environ.get('OFLY_LBFGS', 'twoloop')} if={os.environ.get('OFLY_REBUILD_IF', '1')}] minimise N={len(ids)}: {t1*1e3:.1f} ms, evals {c1[0,0]}, {t1/c1[0,0]*1e6:.1f} us/tick")
 P, A = inputs.perturbed_batch(rmin[0], ex, len(ids) - 1, R, seed=5)
 sR = fly.System(data, fly.Box(tuple(ex)), ids, replicas=R)
 for _ in range(rep):

@@ -187,17 +187,17 @@ def test_host_loop_equals_device_loop(gpu, small_cell):
 
 
 def test_single_pass_lbfgs_equals_two_loop(gpu, otab, small_cell):
-    """The default L-BFGS step (Gram entries, two passes per step: search.cuh newton_step_gram) against the
-    pass-per-pair two-loop recursion (OFLY_LBFGS=twoloop, the literal lbfgs_core.cpp:29-87 order): the two
-    round alpha/beta differently, so trajectories agree to rounding: same exits, same saddles."""
+    """The optional two-pass Gram L-BFGS step (OFLY_LBFGS=gram, search.cuh newton_step_gram) against the default, the literal
+    pass-per-pair two-loop recursion of lbfgs_core.cpp:29-87: the two round alpha/beta differently, so trajectories agree to
+    rounding: same exits, same saddles."""
     fly, ctx, data = gpu
     base, ex, ids, fz, osys, r0, P, A = small_cell
     pot = fly.Generic(data)
     s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=len(P))
-    new = fly.Dimer().find_sp(s, P, A, r0, pot)
-    os.environ["OFLY_LBFGS"] = "twoloop"
+    old = fly.Dimer().find_sp(s, P, A, r0, pot)
+    os.environ["OFLY_LBFGS"] = "gram"
     try:
-        old = fly.Dimer().find_sp(s, P, A, r0, pot)
+        new = fly.Dimer().find_sp(s, P, A, r0, pot)
     finally:
         del os.environ["OFLY_LBFGS"]
     assert new[2].tolist() == old[2].tolist()
