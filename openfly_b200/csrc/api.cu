@@ -528,7 +528,7 @@ void ofly_batch_destroy(ofly_batch *b) {
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   if (b->sibling) ofly_batch_destroy(b->sibling), b->sibling = nullptr;
-  b->search_graph.reset();
+  for (auto &g : b->search_graph) g.reset();
   b->type.release(), b->frozen.release(), b->pos4.release(), b->img_pos.release(), b->nbr.release(), b->nbr16.release(), b->cell_items.release();
   b->cnt.release(), b->cell_of.release(), b->cell_count.release(), b->cell_start.release(), b->fault.release(), b->sel_all.release();
   b->stage_a.release(), b->stage_b.release(), b->stage_c.release(), b->scratch.release(), b->search_ws.release();

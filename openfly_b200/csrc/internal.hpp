@@ -116,7 +116,7 @@ struct ofly_batch {
   std::vector<uint8_t> frozen_host;
   std::vector<ofly::DevBuf<char>> io_pool;                   // device staging of the host-pointer search calls
   std::vector<int> fault_host;
-  ofly_search_graph search_graph;
+  ofly_search_graph search_graph[3];  // one per stage of the device-side loop (shrinking launch grids)
   ofly_batch *sibling = nullptr;  // same system with one more frozen atom (mech_api.cu: the relaxations of do_adj_min)
   long sibling_atom = -1;
 };

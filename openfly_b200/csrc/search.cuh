@@ -111,6 +111,7 @@ namespace ofly {
     int *active, *rebuild;  // [R] selection lists
     int *flags;             // [R] per entry of `active`: bit 0 still active, bit 1 wants a rebuild (written by its team)
     int max_ticks;
+    int exit_below;  // the device-side loop of this graph ends once at most this many replicas are active (0: runs to the end)
     int use_cond;
     unsigned long long *trace;  // tuning aid (OFLY_TRACE): [0] = count, then (mark, globaltimer ns) pairs of replica trace_replica
     int trace_replica, trace_cap;
@@ -1246,7 +1247,7 @@ namespace ofly {
           P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;
           P.ctl->kernels += 3 + ((!P.use_cond_rebuild || nr > 0) ? 5 : 0);
           __threadfence();
-          if (P.use_cond) cudaGraphSetConditional(P.cond, (na > 0 && tick <= P.max_ticks) ? 1u : 0u);
+          if (P.use_cond) cudaGraphSetConditional(P.cond, (na > P.exit_below && tick <= P.max_ticks) ? 1u : 0u);
           if (P.use_cond_rebuild) cudaGraphSetConditional(P.cond_rebuild, nr > 0 ? 1u : 0u);
           if (P.trace != nullptr) trace_mark(P, P.trace_replica, 0, 95);  // end of the tick's bookkeeping
         }

@@ -107,9 +107,9 @@ namespace ofly {
 
     // One team per replica slot; the teams beyond the list of active replicas leave at once.
     template <int C, int MAXT>
-    void launch_segment(ofly_ctx *ctx, ofly_batch *b, int threads, BatchDev const &B, SearchParams const &P) {
+    void launch_segment(ofly_ctx *ctx, long cap, int threads, BatchDev const &B, SearchParams const &P) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(b->R * C));
+      cfg.gridDim = dim3((unsigned)(cap * C));
       cfg.blockDim = dim3((unsigned)threads);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = ctx->stream;
@@ -136,27 +136,28 @@ namespace ofly {
 
     // One tick = segment, rebuild of the flagged replicas, gradient of the active ones (search.cuh), enqueued in
     // three parts so that the device-side loop can put the rebuild kernels behind an IF node.
-    void enqueue_segment(ofly_batch *b, SearchParams const &P, TeamShape shape) {
+    // `cap`: an upper bound on the replicas still active -- every launch grid of a tick is sized for it.
+    void enqueue_segment(ofly_batch *b, SearchParams const &P, TeamShape shape, long cap) {
       ofly_ctx *ctx = b->ctx;
       BatchDev const &B = b->d;
       switch (shape.cluster) {
         case 16:
-          launch_segment<16, kSegMaxThreads>(ctx, b, shape.threads, B, P);
+          launch_segment<16, kSegMaxThreads>(ctx, cap, shape.threads, B, P);
           break;
         case 8:
-          launch_segment<8, kSegMaxThreads>(ctx, b, shape.threads, B, P);
+          launch_segment<8, kSegMaxThreads>(ctx, cap, shape.threads, B, P);
           break;
         case 4:
-          launch_segment<4, kSegMaxThreads>(ctx, b, shape.threads, B, P);
+          launch_segment<4, kSegMaxThreads>(ctx, cap, shape.threads, B, P);
           break;
         case 2:
-          launch_segment<2, kSegMaxThreads>(ctx, b, shape.threads, B, P);
+          launch_segment<2, kSegMaxThreads>(ctx, cap, shape.threads, B, P);
           break;
         default:
           if (shape.threads <= 128) {
-            launch_segment<1, 128>(ctx, b, shape.threads, B, P);
+            launch_segment<1, 128>(ctx, cap, shape.threads, B, P);
           } else {
-            launch_segment<1, kSegMaxThreads>(ctx, b, shape.threads, B, P);
+            launch_segment<1, kSegMaxThreads>(ctx, cap, shape.threads, B, P);
           }
           break;
       }
@@ -169,31 +170,31 @@ namespace ofly {
       unsigned blocks;  // grid-stride launch: enough blocks for the widest groups
       long slots;       // resident threads of the chip
     };
-    PairGrid pair_grid(ofly_batch *b) {
+    PairGrid pair_grid(ofly_batch *b, long cap) {
       int forced = env_int("OFLY_GROUP", 0);
       if (!(forced == 4 || forced == 8 || forced == 16)) forced = 0;
       const int G = forced ? forced : 16;
-      const size_t tiles = (size_t)b->R * ((b->N + 256 / G - 1) / (256 / G));
+      const size_t tiles = (size_t)cap * ((b->N + 256 / G - 1) / (256 / G));
       return {forced, stride_grid(b->ctx, tiles, env_int("OFLY_PAIR_CTAS", 32)), (long)b->ctx->sm_count * 2048};
     }
 
-    void enqueue_rebuild(ofly_batch *b, SearchParams const &P) {
+    void enqueue_rebuild(ofly_batch *b, SearchParams const &P, long cap) {
       ofly_ctx *ctx = b->ctx;
       cudaStream_t st = ctx->stream;
       BatchDev const &B = b->d;
-      const size_t atoms = (size_t)b->R * b->N;
+      const size_t atoms = (size_t)cap * b->N;
       Sel reb{P.rebuild, &P.ctl->n_rebuild};
       k_nb_canon_count<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb, P.ws, P.ws_stride);
-      k_nb_scan<<<stride_grid(ctx, (size_t)b->R, 2), 1024, 0, st>>>(B, reb);
+      k_nb_scan<<<stride_grid(ctx, (size_t)cap, 2), 1024, 0, st>>>(B, reb);
       k_nb_scatter<<<stride_grid(ctx, (atoms + 255) / 256, 8), 256, 0, st>>>(B, reb);
-      k_nb_sort_cells<<<stride_grid(ctx, ((size_t)b->R * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
+      k_nb_sort_cells<<<stride_grid(ctx, ((size_t)cap * B.grid.ncells + 127) / 128, 16), 128, 0, st>>>(B, reb);
       if (B.tile.n_tiles > 0) {  // cell-tiled build (tile.cuh): same rows, candidates tested from shared memory
         OFLY_CUDA(tile_prepare());
-        tile_launch_build(B, reb, stride_grid(ctx, (size_t)b->R * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st);
+        tile_launch_build(B, reb, stride_grid(ctx, (size_t)cap * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st);
         OFLY_CUDA(cudaGetLastError());
         return;
       }
-      const PairGrid pg = pair_grid(b);
+      const PairGrid pg = pair_grid(b, cap);
       switch (pg.forced) {
         case 16:
           k_nb_build<16><<<pg.blocks, 256, 0, st>>>(B, reb);
@@ -211,7 +212,7 @@ namespace ofly {
       OFLY_CUDA(cudaGetLastError());
     }
 
-    void enqueue_gradient(ofly_batch *b, SearchParams const &P) {
+    void enqueue_gradient(ofly_batch *b, SearchParams const &P, long cap) {
       cudaStream_t st = b->ctx->stream;
       BatchDev const &B = b->d;
       TablesDev const &T = b->tables->dev;
@@ -220,12 +221,12 @@ namespace ofly {
       const size_t goff_stride = sizeof(RepState) / sizeof(unsigned long long);
       if (B.tile.n_tiles > 0) {  // cell-tiled passes (tile.cuh): same bits as the row kernels
         OFLY_CUDA(tile_prepare());
-        tile_launch_gradient(B, T, act, stride_grid(ctx_of(b), (size_t)b->R * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st, P.ws,
+        tile_launch_gradient(B, T, act, stride_grid(ctx_of(b), (size_t)cap * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st, P.ws,
                              P.ws_stride, goff, goff_stride);
         OFLY_CUDA(cudaGetLastError());
         return;
       }
-      const PairGrid pg = pair_grid(b);
+      const PairGrid pg = pair_grid(b, cap);
       switch (pg.forced) {
         case 16:
           k_eam_rho<16><<<pg.blocks, 256, 0, st>>>(B, T, act);
@@ -247,10 +248,10 @@ namespace ofly {
       OFLY_CUDA(cudaGetLastError());
     }
 
-    void enqueue_tick(ofly_batch *b, SearchParams const &P, TeamShape shape) {
-      enqueue_segment(b, P, shape);
-      enqueue_rebuild(b, P);
-      enqueue_gradient(b, P);
+    void enqueue_tick(ofly_batch *b, SearchParams const &P, TeamShape shape, long cap) {
+      enqueue_segment(b, P, shape, cap);
+      enqueue_rebuild(b, P, cap);
+      enqueue_gradient(b, P, cap);
     }
 
     // Ends a capture that an exception interrupted, then rethrows.
@@ -271,12 +272,12 @@ namespace ofly {
     };
 
     // Everything a captured tick depends on: the kernels' by-value arguments, the launch shapes and the graph's form.
-    std::vector<char> graph_key(ofly_batch *b, SearchParams const &P, TeamShape shape, bool nested) {
-      const PairGrid pg = pair_grid(b);
+    std::vector<char> graph_key(ofly_batch *b, SearchParams const &P, TeamShape shape, bool nested, long cap) {
+      const PairGrid pg = pair_grid(b, cap);
       std::vector<char> k;
       auto put = [&k](const void *p, size_t n) { k.insert(k.end(), (const char *)p, (const char *)p + n); };
       put(&P, sizeof P), put(&b->d, sizeof b->d), put(&b->tables->dev, sizeof b->tables->dev);
-      put(&shape, sizeof shape), put(&pg, sizeof pg), put(&nested, sizeof nested);
+      put(&shape, sizeof shape), put(&pg, sizeof pg), put(&nested, sizeof nested), put(&cap, sizeof cap);
       return k;
     }
 
@@ -287,11 +288,11 @@ namespace ofly {
     // The instantiated graph is kept in the batch and reused while the key above is unchanged (a Master calls with the
     // same buffers batch after batch); the conditional handles are part of the kernels' arguments, so they are kept too.
     // Returns false if the graph could not be constructed (nothing was launched).
-    bool try_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, bool nested) {
+    bool try_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, bool nested, long grid_cap, int level) {
       ofly_ctx *ctx = b->ctx;
-      ofly_search_graph &g = b->search_graph;
+      ofly_search_graph &g = b->search_graph[level];
       P.use_cond = 0, P.use_cond_rebuild = 0, P.cond = cudaGraphConditionalHandle{}, P.cond_rebuild = cudaGraphConditionalHandle{};
-      std::vector<char> key = graph_key(b, P, shape, nested);
+      std::vector<char> key = graph_key(b, P, shape, nested, grid_cap);
       const bool reuse = g.exec != nullptr && g.key == key && !std::getenv("OFLY_NO_GRAPH_CACHE");
       if (!reuse) {
         g.reset();
@@ -315,7 +316,7 @@ namespace ofly {
           {
             OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
             CaptureScope cap(ctx->stream);
-            enqueue_segment(b, P, shape);
+            enqueue_segment(b, P, shape, grid_cap);
             if (nested) {
               cudaStreamCaptureStatus status;
               const cudaGraphNode_t *deps = nullptr;
@@ -331,15 +332,15 @@ namespace ofly {
               if_body = ip.conditional.phGraph_out[0];
               OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
             } else {
-              enqueue_rebuild(b, P);
+              enqueue_rebuild(b, P, grid_cap);
             }
-            enqueue_gradient(b, P);
+            enqueue_gradient(b, P, grid_cap);
             cap.end();
           }
           if (nested) {
             OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, if_body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
             CaptureScope cap(ctx->stream);
-            enqueue_rebuild(b, P);
+            enqueue_rebuild(b, P, grid_cap);
             cap.end();
           }
           OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
@@ -358,11 +359,34 @@ namespace ofly {
       return true;
     }
 
-    void run_device_loop(ofly_batch *b, SearchParams P, TeamShape shape) {
+    // The device-side loop in up to three stages with shrinking launch grids. A tick's kernels are launched for an upper bound
+    // on the active replicas (teams and blocks beyond the work leave at once, but they still have to be launched: with 1024
+    // slots, 35 of the 72 us of a late tick with one 432-atom replica left were spent between the kernels, profiles/). A graph
+    // cannot change its grids, so a stage's loop ends once the active count has fallen to the next stage's bound and the host
+    // launches the next, smaller graph (a few tens of microseconds, twice per call). Results do not depend on the staging.
+    void run_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, long n0) {
+      ofly_ctx *ctx = b->ctx;
       char const *v = std::getenv("OFLY_REBUILD_IF");
-      const bool nested = !(v && std::string(v) == "0");
-      if (nested && try_device_loop(b, P, shape, true)) return;
-      try_device_loop(b, P, shape, false);
+      bool nested = !(v && std::string(v) == "0");
+      long caps[3] = {n0, 0, 0};
+      int levels = 1;
+      if (env_int("OFLY_STAGES", 1)) {
+        for (; levels < 3 && caps[levels - 1] >= 32; levels++) caps[levels] = (caps[levels - 1] + 7) / 8;
+      }
+      long active = n0;
+      for (int L = 0; L < levels && active > 0; L++) {
+        if (L + 1 < levels && active <= caps[L + 1]) continue;  // already small enough for the next stage
+        P.exit_below = L + 1 < levels ? (int)caps[L + 1] : 0;
+        if (!(nested && try_device_loop(b, P, shape, true, caps[L], L))) {
+          nested = false;
+          try_device_loop(b, P, shape, false, caps[L], L);
+        }
+        Control c{};
+        OFLY_CUDA(cudaMemcpyAsync(&c, P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+        OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
+        active = c.n_active;
+        if (c.tick > P.max_ticks) break;
+      }
     }
 
     // Fallback / profiling mode (OFLY_SEARCH_LOOP=host): plain launches, the host looks at the active
@@ -372,7 +396,7 @@ namespace ofly {
       P.use_cond = 0;
       Control c{};
       for (;;) {
-        for (int t = 0; t < kHostLoopTicks; t++) enqueue_tick(b, P, shape);
+        for (int t = 0; t < kHostLoopTicks; t++) enqueue_tick(b, P, shape, b->R);
         OFLY_CUDA(cudaMemcpyAsync(&c, P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
         OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
         if (c.n_active == 0 || c.tick > P.max_ticks + 1) break;
@@ -481,7 +505,7 @@ namespace ofly {
         k_search_init<<<(unsigned)std::min<long>((n_queue + 255) / 256, 1024), 256, 0, ctx->stream>>>(P, (int)n0);
         OFLY_CUDA(cudaGetLastError());
         if (device_loop) {
-          run_device_loop(b, P, shape);
+          run_device_loop(b, P, shape, n0);
         } else {
           run_host_loop(b, P, shape);
         }

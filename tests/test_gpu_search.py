@@ -410,3 +410,24 @@ def test_search_on_tile_path_equals_row_path(gpu, small_cell):
             del os.environ["OFLY_TILES"]
     for x, y in zip(res["1"], res["0"]):
         assert np.array_equal(x, y)
+
+
+def test_staged_device_loop_equals_single_graph(gpu, small_cell, oracle_lib):
+    """The device-side loop runs in stages with shrinking launch grids (64 -> 8 -> 1 bound on the active replicas); OFLY_STAGES=0
+    keeps one graph for the whole call: bit-identical records."""
+    fly, ctx, data = gpu
+    base, ex, ids, fz, osys, r0, P8, A8 = small_cell
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (8, 3, 3, 4), rep) for rep in range(80)]
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    pot = fly.Generic(data)
+    s = fly.System(data, fly.Box(tuple(ex)), ids, fz, replicas=64)  # queue of 80 through 64 slots: refill, then three stages
+    staged = fly.Dimer().find_sp(s, P, A, r0, pot)
+    os.environ["OFLY_STAGES"] = "0"
+    try:
+        single = fly.Dimer().find_sp(s, P, A, r0, pot)
+    finally:
+        del os.environ["OFLY_STAGES"]
+    again = fly.Dimer().find_sp(s, P, A, r0, pot)
+    s.close()
+    for x, y, z in zip(staged, single, again):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
