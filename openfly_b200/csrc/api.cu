@@ -2,6 +2,7 @@
 // potential::Generic entry points. The search entry points live in search_api.cu.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
@@ -787,10 +788,12 @@ namespace ofly {
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
       de.release();
       OFLY_CUDA(e);
+      if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: eigenvalues of %d matrices (n = %d) by the own kernel\n", count, n3);
       return;
     }
     Cusolver &cs = cusolver();
     if (!cs.ok()) throw Error(OFLY_ERR_CUDA, "libcusolver could not be loaded (needed for the dense symmetric eigenvalue solve)");
+    if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: eigenvalues of %d matrices (n = %d) by cuSOLVER\n", count, n3);
     const int lanes = std::max(1, std::min(std::min(count, env_int("OFLY_SOLVER_LANES", 4)), 16));
     if (!ctx->solver_fork) OFLY_CUDA(cudaEventCreateWithFlags(&ctx->solver_fork, cudaEventDisableTiming));
     while ((int)ctx->solver.size() < lanes) {

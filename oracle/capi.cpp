@@ -1,3 +1,5 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+// A restatement of algorithms of openFLY (ConorWilliams/openFLY, GPL-3.0-or-later); see LICENSE.
 // TEST INFRASTRUCTURE ONLY -- C entry points over fly_oracle.hpp so that tests/ and bench.py's
 // cpu_baseline / --impl reference legs can drive the CPU oracle through ctypes.
 // Nothing under openfly_b200/ may load this library.

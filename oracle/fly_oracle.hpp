@@ -1,3 +1,5 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+// A restatement of algorithms of openFLY (ConorWilliams/openFLY, GPL-3.0-or-later); see LICENSE.
 // TEST INFRASTRUCTURE ONLY -- CPU oracle for the openFLY force-evaluation hot path.
 //
 // This header is an Eigen-free C++17 restatement of the reference's algorithms for the path

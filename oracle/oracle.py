@@ -1,3 +1,4 @@
+# SPDX-License-Identifier: GPL-3.0-or-later
 """TEST INFRASTRUCTURE ONLY -- ctypes view of the CPU oracle (oracle/liboracle*.so).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
