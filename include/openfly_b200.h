@@ -128,6 +128,12 @@ int ofly_neigh_mean_count(ofly_batch *b, double *mean);
 int ofly_neigh_for_atom(ofly_batch *b, long replica, long atom, double r_cut, int *idx_host, double *r_host, double *dr_host, long cap,
                         long *count);
 
+/* The same for EVERY atom of a replica in one pass -- what Catalogue::rebuild_impl / rebuild_geo_from_nl (src/env/catalogue.cpp:80-96)
+ * and DetectVacancies (src/utility/lattice.cpp:69-84) loop for: CSR output, atom i's hits at [offsets[i], offsets[i+1]). offsets: [N+1]
+ * (always written); idx / r: [cap], dr: [cap][3] (skipped when NULL or cap < *total: call once for the size, again with buffers). */
+int ofly_neigh_within_all(ofly_batch *b, long replica, double r_cut, long *offsets_host, int *idx_host, double *r_host, double *dr_host,
+                          long cap, long *total);
+
 /* ---- potential::Generic (EAM) over the batch's current list ---------------------------------- */
 
 /* energy (eam.cpp:33-51): out [R]. */

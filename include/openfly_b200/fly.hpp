@@ -162,6 +162,9 @@ namespace fly_b200 {
   };
 
   namespace neigh {
+    // NOTE: every List, LBFGS and Dimer made on one System shares that System's single device list: a List is valid until the
+    // next rebuild / minimise / find_sp on the same System, by whomever. (The reference's objects each own their list; so do
+    // the classes of include/openfly_b200/libfly.hpp, which is the surface to use for reference-style code.)
     class List {
     public:
       static constexpr long MAX_GHOST_RATIO = 26;  // list.hpp:78
@@ -273,6 +276,7 @@ namespace fly_b200 {
                                           status.data(), nullptr));
         for (int s : status) {
           if (s == -5) throw OutOfBounds("x is outside tabulated region");
+          if (s == -7) throw RuntimeError("minimisation ended without a verdict (tick budget exhausted)");
           if (s < 0) throw RuntimeError("neighbour capacity fault");
         }
         if (failed) failed->assign(status.begin(), status.end());
@@ -318,6 +322,7 @@ namespace fly_b200 {
         for (int c : code) {
           if (c == -5 && throw_oob) throw OutOfBounds("x is outside tabulated region");
           if (c == -6) throw RuntimeError("neighbour capacity fault");
+          if (c == -7) throw RuntimeError("search ended without a verdict (tick budget exhausted)");
           out.push_back(static_cast<Exit>(c));
         }
         return out;

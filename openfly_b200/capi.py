@@ -122,6 +122,7 @@ SIGNATURES = {
                                                 C.c_long, C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
     "ofly_eam_hessian_eigenvalues": (C.c_int, [_vp, C.c_long, C.c_int, _dp]),
     "ofly_neigh_for_atom": (C.c_int, [_vp, C.c_long, C.c_long, C.c_double, _ip, _dp, _dp, C.c_long, _lp]),
+    "ofly_neigh_within_all": (C.c_int, [_vp, C.c_long, C.c_double, _lp, _ip, _dp, _dp, C.c_long, _lp]),
     "ofly_master_perturb": (C.c_int, [_vp, C.c_long, _dp, C.c_long, C.c_double, _dp, _dp, _dp, _dp]),
     "ofly_skmc_relax_step": (C.c_int, [_vp, C.POINTER(LbfgsOptions), _dp, _dp, _dp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),

@@ -237,6 +237,49 @@ namespace ofly {
       if (threadIdx.x == 0) *count = found;
     }
 
+    // for_neighbours of EVERY atom of a replica within r_cut (the loop of Catalogue::rebuild_impl / rebuild_geo_from_nl,
+    // src/env/catalogue.cpp:80-96, and of DetectVacancies, src/utility/lattice.cpp:69-84): a sub-warp of 8 lanes per atom.
+    // FILL = false: counts[i] = hits; FILL = true: (index, r, dr) written from offsets[i], in stored order.
+    template <bool FILL>
+    __global__ void __launch_bounds__(256) k_neigh_within_all(BatchDev B, int r, double r_cut_sq, int *__restrict__ counts,
+                                                             const long *__restrict__ offsets, int *__restrict__ idx, double *__restrict__ dist,
+                                                             double *__restrict__ dr) {
+      constexpr int G = 8;
+      const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G), lane = threadIdx.x % G;
+      if (i >= B.N) return;
+      const unsigned gmask = group_mask<G>();
+      const int sub = ((threadIdx.x & 31) / G) * G;
+      const double4 *pos = B.pos4 + (size_t)r * B.N;
+      const uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
+      const int n = B.cnt[(size_t)r * B.N + i];
+      const double4 pi = pos[i];
+      long found = 0;
+      for (int k0 = 0; k0 < n; k0 += G) {
+        const int k = k0 + lane;
+        bool hit = false;
+        int j = 0;
+        double dx = 0, dy = 0, dz = 0, r2 = 0;
+        if (k < n) {
+          const uint32_t e = row[k];
+          j = (int)(e & kIdxMask);
+          const int code = (int)((e >> 24) & 31u);
+          const double4 pj = pos[j];
+          dx = (pj.x + shift_of(code % 3, B.box.L[0])) - pi.x;
+          dy = (pj.y + shift_of((code / 3) % 3, B.box.L[1])) - pi.y;
+          dz = (pj.z + shift_of(code / 9, B.box.L[2])) - pi.z;
+          r2 = (dx * dx + dy * dy) + dz * dz;
+          hit = r2 < r_cut_sq;
+        }
+        const unsigned bal = __ballot_sync(gmask, hit) >> sub;
+        if (FILL && hit) {
+          const long w = offsets[i] + found + __popc(bal & ((1u << lane) - 1u));
+          idx[w] = j, dist[w] = sqrt(r2), dr[3 * w] = dx, dr[3 * w + 1] = dy, dr[3 * w + 2] = dz;
+        }
+        found += __popc(bal & ((1u << G) - 1u));
+      }
+      if (!FILL && lane == 0) counts[i] = (int)found;
+    }
+
     // Master::perturb (find.cpp:1147-1214) for one start state per CTA. z: this state's standard normal draws, [N][6]
     // (three for the position, three for the axis of every atom; only those of atoms inside r_pert are used).
     __global__ void __launch_bounds__(kMechThreads) k_master_perturb(BatchDev B, int centre, double r_pert, const double *__restrict__ in_min,
@@ -425,6 +468,49 @@ int ofly_neigh_for_atom(ofly_batch *b, long replica, long atom, double r_cut, in
       idx_host[k] = hi[(size_t)k + 1], r_host[k] = hv[(size_t)k];
       for (int c = 0; c < 3; c++) dr_host[3 * k + c] = hv[K + 3 * (size_t)k + c];
     }
+  });
+}
+
+int ofly_neigh_within_all(ofly_batch *b, long replica, double r_cut, long *offsets_host, int *idx_host, double *r_host, double *dr_host,
+                          long cap, long *total) {
+  return guarded([&] {
+    require(b && offsets_host && total, "null argument");
+    require(b->built, "for_neighbours before rebuild()");
+    require(replica >= 0 && replica < b->R, "replica out of range");
+    require(r_cut <= b->r_list, "r_cut is bigger then than the internal r_cut");  // list.hpp:141-143
+    OFLY_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const size_t N = (size_t)b->N;
+    DevBuf<int> d_cnt, d_idx;
+    DevBuf<long> d_off;
+    DevBuf<double> d_val;
+    struct Rel {
+      DevBuf<int> *a, *b2;
+      DevBuf<long> *c;
+      DevBuf<double> *d;
+      ~Rel() { a->release(), b2->release(), c->release(), d->release(); }
+    } rel{&d_cnt, &d_idx, &d_off, &d_val};
+    d_cnt.reserve(N), d_off.reserve(N + 1);
+    const unsigned grid = (unsigned)((N * 8 + 255) / 256);
+    k_neigh_within_all<false><<<grid, 256, 0, st>>>(b->d, (int)replica, r_cut * r_cut, d_cnt.p, nullptr, nullptr, nullptr, nullptr);
+    std::vector<int> cnt(N);
+    OFLY_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.p, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaStreamSynchronize(st));
+    offsets_host[0] = 0;
+    for (size_t i = 0; i < N; i++) offsets_host[i + 1] = offsets_host[i] + cnt[i];
+    const long tot = offsets_host[N];
+    *total = tot;
+    b->ctx->launches++;
+    if (tot == 0 || !idx_host || !r_host || !dr_host || cap < tot) return;  // sizes only (or the caller's buffers are too small)
+    d_idx.reserve((size_t)tot), d_val.reserve(4 * (size_t)tot);
+    OFLY_CUDA(cudaMemcpyAsync(d_off.p, offsets_host, (N + 1) * sizeof(long), cudaMemcpyHostToDevice, st));
+    k_neigh_within_all<true><<<grid, 256, 0, st>>>(b->d, (int)replica, r_cut * r_cut, nullptr, d_off.p, d_idx.p, d_val.p, d_val.p + tot);
+    OFLY_CUDA(cudaGetLastError());
+    b->ctx->launches++;
+    OFLY_CUDA(cudaMemcpyAsync(idx_host, d_idx.p, (size_t)tot * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaMemcpyAsync(r_host, d_val.p, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaMemcpyAsync(dr_host, d_val.p + tot, 3 * (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OFLY_CUDA(cudaStreamSynchronize(st));
   });
 }
 

@@ -191,8 +191,10 @@ class List:
             raise OflyError(capi.OFLY_ERR_INVALID, f"{num_threads} is not a valid number of threads for rebuild()")
         p = self.sys._vec(positions)
         check(self.sys.ctx.lib.ofly_neigh_rebuild(self.sys.h, self.r_cut, ptr(p, _dp)))
+        self.sys._list_owner = self  # the System holds ONE device list: whoever rebuilt last owns it (see Generic._owned)
 
     def update(self, delta) -> None:
+        Generic._owned(self)
         d = self.sys._vec(delta)
         check(self.sys.ctx.lib.ofly_neigh_update(self.sys.h, ptr(d, _dp)))
 
@@ -232,6 +234,19 @@ class List:
         for k in range(len(idx)):
             f(int(idx[k]), float(r[k]), dr[k])
 
+    def neighbours_within(self, r_cut: float, replica: int = 0):
+        """for_neighbours of every atom in one device pass: (offsets[N+1], index[total], r[total], dr[total, 3]) in CSR form."""
+        lib, s = self.sys.ctx.lib, self.sys
+        if r_cut > self.r_cut:
+            raise OflyError(capi.OFLY_ERR_INVALID, f"r_cut={r_cut} is bigger then than the internal r_cut={self.r_cut}")
+        off = np.zeros(s.N + 1, dtype=np.int64)
+        tot = C.c_long()
+        check(lib.ofly_neigh_within_all(s.h, replica, r_cut, ptr(off, _lp), None, None, None, 0, C.byref(tot)))
+        n = max(tot.value, 1)
+        idx, r, dr = np.zeros(n, dtype=np.int32), np.zeros(n), np.zeros((n, 3))
+        check(lib.ofly_neigh_within_all(s.h, replica, r_cut, ptr(off, _lp), ptr(idx, _ip), ptr(r, _dp), ptr(dr, _dp), n, C.byref(tot)))
+        return off, idx[:tot.value], r[:tot.value], dr[:tot.value]
+
     def neighbours_of(self, i: int, r_cut: float, replica: int = 0):
         """(real index[n], r[n], dr[n, 3]) of atom i's neighbours within r_cut, in stored order."""
         cap = 1024
@@ -257,18 +272,30 @@ class Generic:
     def r_cut(self) -> float:
         return self.data.rcut()
 
+    @staticmethod
+    def _owned(nl: List) -> None:
+        """A System holds one device list shared by every List / LBFGS / Dimer made on it (unlike the reference, where each object
+        owns its own; the C++ surface include/openfly_b200/libfly.hpp does own one per object). Evaluating a potential over a
+        List whose device state another List or a search has replaced since would silently use the wrong positions: refuse."""
+        if getattr(nl.sys, "_list_owner", None) is not nl:
+            raise OflyError(capi.OFLY_ERR_INVALID, "this List's device state was replaced (another List.rebuild or a minimise / find_sp "
+                                                   "call on the same System): rebuild it first")
+
     def energy(self, nl: List, num_threads: int = 1) -> np.ndarray:
+        self._owned(nl)
         out = np.zeros(nl.sys.R, dtype=np.float64)
         check(nl.sys.ctx.lib.ofly_eam_energy(nl.sys.h, ptr(out, _dp)))
         return out
 
     def gradient(self, nl: List, num_threads: int = 1) -> np.ndarray:
+        self._owned(nl)
         out = np.zeros((nl.sys.R, nl.sys.N, 3), dtype=np.float64)
         check(nl.sys.ctx.lib.ofly_eam_gradient(nl.sys.h, ptr(out, _dp)))
         return out
 
     def hessian(self, nl: List, replica: int = 0, mass_weight: bool = False, num_threads: int = 1) -> np.ndarray:
         """Dense (3N, 3N) array; only the lower triangle is meaningful (system::Hessian)."""
+        self._owned(nl)
         n3 = 3 * nl.sys.N
         out = np.zeros((n3, n3), dtype=np.float64)
         check(nl.sys.ctx.lib.ofly_eam_hessian(nl.sys.h, replica, 1 if mass_weight else 0, ptr(out, _dp)))
@@ -276,6 +303,7 @@ class Generic:
 
     def hessian_batch(self, nl: List, mass_weight: bool = False) -> np.ndarray:
         """[R, 3N, 3N]: the Hessians of every replica from one launch (lower triangles meaningful)."""
+        self._owned(nl)
         n3 = 3 * nl.sys.N
         out = np.zeros((nl.sys.R, n3, n3), dtype=np.float64)
         check(nl.sys.ctx.lib.ofly_eam_hessian_batch(nl.sys.h, 1 if mass_weight else 0, ptr(out, _dp)))
@@ -283,6 +311,7 @@ class Generic:
 
     def hessian_eigenvalues(self, nl: List, replica: int = 0, mass_weight: bool = True) -> np.ndarray:
         """system::Hessian::eigenvalues() of the (mass-weighted) Hessian, solved on the device: only 3N doubles return."""
+        self._owned(nl)
         out = np.zeros(3 * nl.sys.N, dtype=np.float64)
         check(nl.sys.ctx.lib.ofly_eam_hessian_eigenvalues(nl.sys.h, replica, 1 if mass_weight else 0, ptr(out, _dp)))
         return out
@@ -326,6 +355,7 @@ class LBFGS:
         """positions: [Q, N, 3]; Q == system.R is the reference's batch, any other Q streams through the R slots."""
         p = system._queue(positions)
         Q = p.shape[0]
+        system._list_owner = None  # the search rebuilds the System's device list at its own radius
         out_r = np.zeros_like(p)
         out_g = np.zeros_like(p)
         status = np.zeros(Q, dtype=np.int32)
@@ -355,6 +385,7 @@ class Dimer:
         p = system._queue(positions)
         ax = system._queue(axis)
         Q = p.shape[0]
+        system._list_owner = None  # the search rebuilds the System's device list at its own radius
         if ax.shape != p.shape:
             raise OflyError(capi.OFLY_ERR_INVALID, "positions and axes differ in shape")
         mn = f64(in_min).reshape(system.N, 3)

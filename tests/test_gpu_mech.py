@@ -263,3 +263,48 @@ def test_skmc_relax_step(gpu, c3, oracle_lib):
     assert abs(got["E0"] - e0) < 1e-9 and abs(got["Ef"] - ef) < 1e-8
     assert np.abs(got["rel_recon"] - rel).max() < 1e-6
     assert abs(got["dR"] - np.sqrt(((rel - raw) ** 2).sum())) < 1e-5
+
+
+def test_neighbourhoods_of_every_atom_in_one_pass(gpu, c3):
+    """ofly_neigh_within_all (the loop of Catalogue::rebuild_impl, src/env/catalogue.cpp:80-96, at r_env): CSR of every atom's
+    neighbours within r_cut against the oracle's for_neighbours atom by atom."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    nl = fly.List(s, 5.2)
+    nl.rebuild(sps[1])
+    osys.rebuild(5.2, sps[1])
+    off, idx, r, dr = nl.neighbours_within(5.2)
+    assert off[0] == 0 and off[-1] == len(idx)
+    for atom in list(range(0, len(ids), 37)) + [len(ids) - 1]:
+        o_idx, o_r, o_dr = osys.for_neighbours(atom, 5.2)
+        a = slice(off[atom], off[atom + 1])
+        p, q = np.lexsort((r[a], idx[a])), np.lexsort((o_r, o_idx))
+        assert np.array_equal(idx[a][p], np.asarray(o_idx)[q])
+        assert np.abs(r[a][p] - np.asarray(o_r)[q]).max() < 1e-12 and np.abs(dr[a][p] - np.asarray(o_dr)[q]).max() < 1e-12
+        one = nl.neighbours_of(atom, 5.2)
+        assert np.array_equal(one[0], idx[a]) and np.array_equal(one[1], r[a])  # same order as the single-atom call
+    off2, idx2, _, _ = nl.neighbours_within(3.0)
+    assert off2[-1] < off[-1]
+    s.close()
+
+
+def test_python_list_refuses_stale_device_state(gpu, c3):
+    """fly.py's System holds ONE device list (fly.hpp likewise; libfly.hpp owns one per List): a List whose device state was
+    replaced by another List or by a search must not be evaluated silently on the wrong positions."""
+    fly, ctx, data = gpu
+    otab, osys, ex, ids, fz, r0, sps, axs = c3
+    s = fly.System(data, fly.Box(tuple(ex)), ids)
+    pot = fly.Generic(data)
+    a, b = fly.List(s, data.rcut()), fly.List(s, data.rcut() + 0.4)
+    a.rebuild(r0)
+    e = pot.energy(a)[0]
+    b.rebuild(sps[0])
+    with pytest.raises(fly.OflyError, match="replaced"):
+        pot.energy(a)
+    a.rebuild(r0)
+    assert pot.energy(a)[0] == e
+    fly.LBFGS().minimise(s, sps[0], pot)
+    with pytest.raises(fly.OflyError, match="replaced"):
+        pot.gradient(a)
+    s.close()
