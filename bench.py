@@ -3,8 +3,9 @@
 
 Workload (BASELINE.json configs[1], "C2"): bcc Fe 20x20x20 (a = 2.8553), one vacancy, one H -> 16 000 atoms; dimer saddle
 searches started from Master::perturb-style states around the H atom, 64 of them resident on a GPU at any time.
-One *step* = one environment's worth of searches on every GPU: a queue of 256 start states per GPU (the reference's
-find_n launches batches of 64 until max_searches are done, src/saddle/find.cpp:374-422) streams through the 64 resident
+One *step* = two environments' worth of searches on every GPU: a queue of 512 start states per GPU (the reference's find_n
+launches batches until max_searches = 250 are done per environment, src/saddle/find.cpp:374-422, find.hpp:171, and
+Master::find_mechs runs all new environments of a KMC step concurrently, find.cpp:249-259) streams through the 64 resident
 slots; a slot whose search has finished claims the next start state on the device (ofly_dimer_find_sp_stream), so there is
 no barrier after every 64. All of it -- every neighbour rebuild/update, EAM gradient, rotor and L-BFGS update -- is ONE
 CUDA-graph launch whose body (a tick: vector algebra of every active replica, rebuilds, one gradient evaluation) repeats on
@@ -19,7 +20,7 @@ the device.
   cpu_baseline / --impl reference: the CPU oracle built with the reference's flags, all host cores, one
            single-threaded search per core exactly like saddle::Master (src/saddle/find.cpp:698,990)
 
-N > 1 (torchrun): ONE global queue of N x 256 searches is sharded by search id (global id g runs on rank g mod N,
+N > 1 (torchrun): ONE global queue of N x 512 searches is sharded by search id (global id g runs on rank g mod N,
 openfly_b200/shard.py), every rank streams its shard through its own GPU, the finished records are merged on the host in id
 order (shard.merge_records) -- no collective on the data path; per-GPU work is fixed as N grows (weak scaling) but every
 rank runs DIFFERENT searches. A strong-scaling leg rides along: BASELINE configs[4], 2048 searches on the 431-atom cell
@@ -42,18 +43,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WEN = os.path.join(ROOT, "data", "wen.eam.fs")
-CELLS, LATTICE, SLOTS, QUEUE = 20, 2.8553, 64, 256
+CELLS, LATTICE, SLOTS, QUEUE = 20, 2.8553, 64, 512
 C5_TOTAL, C5_SLOTS = 2048, 1024
 METRIC, UNIT = "eam_atom_gradient_evals_per_s", "atom-evals/s"
 WORKLOAD = ("C2: bcc Fe 20^3 (a=2.8553) - 1 vacancy + 1 H = 16000 atoms, Wen Fe-H EAM, dimer searches (Dimer::find_sp, default options) "
-            "from Master::perturb start states: 64 concurrent searches per GPU, 256 queued per GPU and step")
+            "from Master::perturb start states: 64 concurrent searches per GPU, 512 queued per GPU and step")
 CPU_SAMPLE_MAX_STEPS = 40  # translation steps per CPU search in the bounded sample (a full search averages ~45; shorter cuts flatter the CPU: the first steps rarely rebuild the list)
 
 
 def config_dict(seed: int):
     """The same object in both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "atoms": 16000, "resident_searches_per_gpu": SLOTS, "queued_searches_per_gpu_per_step": QUEUE,
-            "multi_gpu": "one global queue of n_gpus x 256 searches sharded by id (g mod n_gpus), no data-path collective, records merged on the host",
+            "multi_gpu": "one global queue of n_gpus x 512 searches sharded by id (g mod n_gpus), no data-path collective, records merged on the host",
             "l2": "inputs larger than L2: neighbour rows 64x16000x104x4 B = 426 MB + 1.1 GB of search vectors vs 126 MB L2; no explicit flush",
             "seed": seed}
 

@@ -170,9 +170,13 @@ namespace ofly {
     const int ti = B.type[i];
     const double4 pi = ld256(pos + i);
     VirtSum<G, 2> acc;
-    for (int k0 = lane * J; k0 < n; k0 += kVirt) {
-      uint32_t e[J];
-      load_entries<J>(row + k0, e);
+    // the entries of the next round are requested before this round's pairs are worked on: the entry load heads the
+    // dependent chain entry -> record -> knot and is the first stall of the kernel (long_scoreboard, profiles/)
+    uint32_t e[J], en[J];
+    int k0 = lane * J;
+    if (k0 < n) load_entries<J>(row + k0, e);
+    for (; k0 < n; k0 += kVirt) {
+      if (k0 + kVirt < n) load_entries<J>(row + k0 + kVirt, en);
 #pragma unroll
       for (int j = 0; j < J; j++) {
         if (k0 + j < n) {
@@ -180,6 +184,8 @@ namespace ofly {
           rho_term<WITH_V>(T, ti, g, acc.a[j][0], acc.a[j][1], oob);
         }
       }
+#pragma unroll
+      for (int j = 0; j < J; j++) e[j] = en[j];
     }
     double tot[2];
     acc.total(tot);
@@ -199,9 +205,11 @@ namespace ofly {
     const double4 pi = ld256(pos + i);
     const double Fi = pi.w;
     VirtSum<G, 3> acc;
-    for (int k0 = lane * J; k0 < n; k0 += kVirt) {
-      uint32_t e[J];
-      load_entries<J>(row + k0, e);
+    uint32_t e[J], en[J];  // entries one round ahead (see eam_rho_atom)
+    int k0 = lane * J;
+    if (k0 < n) load_entries<J>(row + k0, e);
+    for (; k0 < n; k0 += kVirt) {
+      if (k0 + kVirt < n) load_entries<J>(row + k0 + kVirt, en);
 #pragma unroll
       for (int j = 0; j < J; j++) {
         if (k0 + j < n) {
@@ -209,6 +217,8 @@ namespace ofly {
           force_term(T, ti, Fi, g, acc.a[j][0], acc.a[j][1], acc.a[j][2], oob);
         }
       }
+#pragma unroll
+      for (int j = 0; j < J; j++) e[j] = en[j];
     }
     double tot[3];
     acc.total(tot);

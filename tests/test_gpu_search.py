@@ -431,3 +431,18 @@ def test_staged_device_loop_equals_single_graph(gpu, small_cell, oracle_lib):
     s.close()
     for x, y, z in zip(staged, single, again):
         assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+def test_dimer_on_a_two_cta_team_matches_oracle(gpu, otab, oracle_lib):
+    """A 1 458-atom cell (9^3): its 4 374-element vectors run on a cluster of two CTAs (search_api.cu pick_team), the one team
+    shape between the single-CTA cells above and the 16-CTA teams of the C2 batch."""
+    fly, ctx, data = gpu
+    base, ex, ids = bcc_vacancy(9, a=2.855, remove=(1,), hydrogen=True)
+    fz = np.zeros(len(ids), np.uint8)
+    osys = oracle_lib.System(otab, ex)
+    r0, _, failed, _ = osys.minimise(base, ids, fz, threads=8)
+    assert not failed
+    starts = [osys.perturb(r0, fz, len(ids) - 1, (1, 3, 3, 4), rep) for rep in range(4)]
+    P, A = np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts])
+    code, cnt, o_cnt, n_ok = _check_dimer_against_oracle(fly, data, otab, ids, fz, ex, osys, r0, P, A, threads=4)
+    assert n_ok >= 1
