@@ -85,7 +85,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu,clocks.mem")
 
     def __init__(self, device: int):
         self.device, self.proc, self.lines = device, None, []
@@ -107,7 +107,7 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, util, reasons = [], [], [], set()
+        sm, mx, util, mem, pw, reasons = [], [], [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
@@ -116,6 +116,9 @@ class ClockSampler:
                 sm.append(float(f[1])), mx.append(float(f[2]))
                 if len(f) > 8:
                     util.append(float(f[8]))
+                if len(f) > 9:
+                    mem.append(float(f[9]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
@@ -124,7 +127,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "gpu_util_mean": (float(np.mean(util)) if util else None)}
+                "gpu_util_mean": (float(np.mean(util)) if util else None), "sm_mhz_min": float(min(sm)),
+                "mem_mhz_min": (float(min(mem)) if mem else None), "power_w_max": (float(max(pw)) if pw else None)}
 
 
 def c2_cell():
@@ -528,17 +532,21 @@ def c3_environment(ctx, data, pot, dopt, ropt, seed):
     try:
         mech = fly.Mechanisms(data, box, ids, replicas=int(min(max(n_ok, 1), 192)))  # every saddle's Hessian in flight at once
         mech.prefactors(rmin[0], out_r[ok[:2]])  # warm-up
-        t0 = time.perf_counter()
-        res = mech.prefactors(rmin[0], out_r[ok])
-        t_hess = time.perf_counter() - t0
+        with ClockSampler(ctx.device) as mech_clocks:
+            t0 = time.perf_counter()
+            res = mech.prefactors(rmin[0], out_r[ok])
+            t_hess = time.perf_counter() - t0
+            time.sleep(0.3)
+        clk = mech_clocks.summary()
         nus = res["prefactor"][res["valid"] == 1]
         mech.close()
     except fly.OflyError as e:
-        t_hess, nus = None, str(e)
+        t_hess, nus, clk = None, str(e), None
     return {"workload": "C3: 6^3 Fe - vacancy + H (431 atoms), 256 dimer searches of one environment + Hessian / eigenvalues / prefactor per saddle",
             "searches": R, "saddles": n_ok, "search_s": t_search, "searches_per_s": R / t_search,
             "atom_evals_per_s": float(cnt[:, 0].sum()) * len(ids) / t_search, "longest_search_evals": int(cnt[:, 0].max()),
             "hessian_eigen_s": t_hess, "hessian_eigen_ms_per_saddle": (t_hess / max(n_ok, 1) * 1e3) if t_hess else None,
+            "hessian_eigen_clocks": (clk if t_hess else None),
             "prefactors": (int(len(nus)) if not isinstance(nus, str) else nus),
             "median_prefactor_hz": (float(np.median(nus)) if not isinstance(nus, str) and len(nus) else None)}
 

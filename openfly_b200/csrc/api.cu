@@ -721,7 +721,7 @@ namespace ofly {
     launch(b->ctx, k_hess_columns<32>, rows * 32, 256, b->d, b->tables->dev, (const int *)b->hess_sel.p, count, (const double *)b->hess_aux.p,
            b->hess_H.p, hs);
     if (mass_weight) {
-      launch(b->ctx, k_hess_mass_weight, hs, 256, b->hess_H.p, hs, count, (int)b->N, (const uint8_t *)b->type.p, (const double *)b->hess_mass.p);
+      launch(b->ctx, k_hess_mass_weight, n3 * n3, 256, b->hess_H.p, hs, count, (int)b->N, (const uint8_t *)b->type.p, (const double *)b->hess_mass.p);
     }
   }
 

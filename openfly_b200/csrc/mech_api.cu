@@ -11,7 +11,10 @@
 // the Hessians of a chunk are assembled by one launch (hessian.cuh) and solved concurrently.
 // Not covered: the reconstruction test (recon_relax, find.cpp:873-940) -- it needs env::Geometry (nauty), out of scope.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -756,10 +759,17 @@ int ofly_mech_from_saddles(ofly_batch *b, const ofly_mech_options *opt, const of
       }
       for (size_t w0 = 0; w0 < want.size(); w0 += h_chunk) {
         const int cnt = (int)std::min(h_chunk, want.size() - w0);
+        const auto t0 = std::chrono::steady_clock::now();
         assemble_hessians(b, want.data() + w0, cnt, 1);
         collect_faults(b);
+        const auto t1 = std::chrono::steady_clock::now();
         b->hess_eig.reserve((size_t)cnt * n3);
         eigenvalues_dev(ctx, b->hess_H.p, (int)n3, cnt, b->hess_eig.p);
+        if (std::getenv("OFLY_VERBOSE")) {
+          const auto t2 = std::chrono::steady_clock::now();
+          std::fprintf(stderr, "openfly_b200: %d Hessians assembled in %.1f ms, eigenvalues in %.1f ms\n", cnt,
+                       std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+        }
         std::vector<double> freq((size_t)cnt * n3);
         OFLY_CUDA(cudaMemcpy(freq.data(), b->hess_eig.p, freq.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int q = 0; q < cnt; q++) {
