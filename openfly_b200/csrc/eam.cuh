@@ -27,9 +27,11 @@ namespace ofly {
   };
 
   // Geometry of a pair from the neighbour's image position (already shifted) and the centre.
+  // r2 in gnorm_sq's own order, (x x + y y) + z z without contraction (core.hpp:655-680): the second cut-off filter of
+  // for_neighbours (list.hpp:148-150) then admits exactly the reference's pairs, not a set that may differ in the last bit.
   __device__ __forceinline__ void pair_geometry(PairGeom &g, double qx, double qy, double qz, const double4 &pi) {
     g.dx = qx - pi.x, g.dy = qy - pi.y, g.dz = qz - pi.z;
-    g.r2 = fma(g.dz, g.dz, fma(g.dy, g.dy, g.dx * g.dx));
+    g.r2 = norm_sq_rn(g.dx, g.dy, g.dz);
   }
 
   // Decode one neighbour entry and fetch its record from global memory. The image position is pos4[j] + shift, the

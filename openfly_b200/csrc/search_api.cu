@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <vector>
 #include <string>
 
@@ -60,6 +61,8 @@ namespace ofly {
     template <int C>
     int active_clusters(ofly_ctx *ctx) {
       static std::map<int, int> known;
+      static std::mutex known_mutex;  // one host thread per device may be in here at the same time
+      std::lock_guard<std::mutex> lock(known_mutex);
       auto it = known.find(ctx->device);
       if (it != known.end()) return it->second;
       int n = 0;
