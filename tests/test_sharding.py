@@ -80,3 +80,21 @@ def test_two_gloo_ranks_equal_one_process(oracle_lib):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == (True, True, True)
+
+
+def test_bench_start_states_do_not_depend_on_the_sharding():
+    """bench.py draws the start state of global search g from the stream (seed, g): a rank's shard of the global queue is the
+    same set of states whatever the number of ranks, so the N-GPU runs of the scaling bench work on ONE global queue."""
+    import bench
+    from openfly_b200 import inputs, shard
+
+    pos, ex, ids = inputs.iron_hydrogen_cell(3, 2.855, remove=(1,), hydrogen=True)
+    total = 12
+    P, A = bench.start_states(pos, ex, len(ids) - 1, np.arange(total), seed=5)
+    for world in (2, 4):
+        for rank in range(world):
+            gids = shard.replica_ids(total, world, rank)
+            p, a = bench.start_states(pos, ex, len(ids) - 1, gids, seed=5)
+            assert np.array_equal(p, P[gids]) and np.array_equal(a, A[gids])
+    cfg = bench.config_dict(1334)
+    assert cfg["queued_searches_per_gpu_per_step"] == bench.QUEUE and cfg["resident_searches_per_gpu"] == bench.SLOTS
