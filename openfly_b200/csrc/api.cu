@@ -185,7 +185,8 @@ namespace ofly {
     if (b->d.tile.n_tiles > 0) {
       OFLY_CUDA(tile_prepare());
       tile_launch_build(b->d, all, tile_grid(b), st);
-      ctx->launches += 5;
+      launch_order_rows(b->d, all, stride_grid(ctx, (atoms + 7) / 8, 8), st);
+      ctx->launches += 6;
       OFLY_CUDA(cudaGetLastError());
       return;
     }
@@ -206,7 +207,8 @@ namespace ofly {
         k_nb_build<4><<<gg, 256, 0, st>>>(b->d, all);
         break;
     }
-    ctx->launches += 5;
+    launch_order_rows(b->d, all, stride_grid(ctx, (atoms + 7) / 8, 8), st);
+    ctx->launches += 6;
     OFLY_CUDA(cudaGetLastError());
   }
 
@@ -592,7 +594,7 @@ int ofly_neigh_export(ofly_batch *b, long replica, int *counts_host, int *idx_ho
       counts_host[i] = cnt[(size_t)i];
       for (int k = 0; k < cnt[(size_t)i]; k++, w++) {
         if (w < cap) {
-          uint32_t e = rows[(size_t)i * b->d.K + k];
+          uint32_t e = rows[(size_t)i * b->d.K + row_slot(k)];
           idx_host[w] = (int)(e & kIdxMask), shift_host[w] = (int)((e >> 24) & 31u);
         }
       }

@@ -5,6 +5,8 @@
 //                             32 B aligned so one 256-bit load fetches a neighbour's whole record
 //   nbr    [R][N][K] uint32   neighbour entries, atom-major rows: bits 0-23 real index j,
 //                             bits 24-28 image shift code (sx+1)+3(sy+1)+9(sz+1), bits 29-31 type of j.
+//                             A row is ordered by (j, shift) and stored in rounds of 16 entries, each round
+//                             transposed as a 4 x 4 block: the k-th neighbour lives at row[row_slot(k)].
 //                             Ghost atoms are never materialised after the build: the image position
 //                             is pos4[j] + shift*L, which is exactly how the reference created it.
 //   cnt    [R][N]    int32    stored neighbours per atom
@@ -19,6 +21,13 @@ namespace ofly {
   constexpr int kShiftCentre = 13;     // (0,0,0) image
   constexpr uint32_t kIdxMask = 0x00FFFFFFu;
   constexpr int kMaxTypes = 8;
+
+  // Storage slot of the k-th neighbour of a row (and, the map being an involution, the rank of the entry in slot k).
+  // Rounds of 16 entries are stored as transposed 4 x 4 blocks: the four lanes of a sub-warp that vector-load slots
+  // 4t .. 4t+3 of a round work, in their m-th pair, on the CONSECUTIVE ranks 4m .. 4m+3. Rows are ordered by neighbour
+  // index, so the 32 records one warp-wide load instruction gathers (8 consecutive atoms x 4 consecutive neighbours) sit
+  // in a few 128 B lines instead of one line per lane: the L1 data pipe serves a load per distinct line.
+  __host__ __device__ constexpr int row_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
 
   // Fault bits recorded per replica.
   constexpr int kFaultOutOfBounds = 1;  // Spline::OutOfBounds

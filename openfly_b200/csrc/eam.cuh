@@ -107,11 +107,12 @@ namespace ofly {
   }
 
   // ---- per-atom sums whose bits do not depend on the sub-warp width ---------------------------------
-  // A row is consumed in rounds of kVirt = 16 consecutive entries; entry k0 + v of a round belongs to *virtual lane* v, a
-  // virtual lane adds its terms in ascending k, and the 16 partial sums are combined by the butterfly (v, v^1), (v, v^2),
-  // (v, v^4), (v, v^8). A physical sub-warp of G lanes carries J = 16 / G consecutive virtual lanes per thread (lane l owns
-  // v = l J .. l J + J - 1: its entries of a round are contiguous, ONE vector load), folds the low butterfly levels in
-  // registers and does the remaining ones with shuffles. Every G therefore produces the SAME bits, and so does the tile
+  // A row is consumed in rounds of kVirt = 16 storage slots; slot v of a round belongs to *virtual lane* v (the entry it
+  // holds is the round's neighbour of rank row_slot(v), device_common.cuh), a virtual lane adds its terms round after
+  // round, and the 16 partial sums are combined by the butterfly (v, v^1), (v, v^2), (v, v^4), (v, v^8). A physical
+  // sub-warp of G lanes carries J = 16 / G consecutive virtual lanes per thread (lane l owns v = l J .. l J + J - 1: its
+  // entries of a round are contiguous, ONE vector load), folds the low butterfly levels in registers and does the
+  // remaining ones with shuffles. Every G therefore produces the SAME bits, and so does the tile
   // path (tile.cuh), so a replica's energies, forces and trajectory do not depend on how many replicas share its batch
   // (the tick kernels pick G from the active count), on the code path, or on how a batch is sharded over GPUs.
   constexpr int kVirt = 16;
@@ -175,13 +176,13 @@ namespace ofly {
     // the entries of the next round are requested before this round's pairs are worked on: the entry load heads the
     // dependent chain entry -> record -> knot and is the first stall of the kernel (long_scoreboard, profiles/)
     uint32_t e[J], en[J];
-    int k0 = lane * J;
-    if (k0 < n) load_entries<J>(row + k0, e);
-    for (; k0 < n; k0 += kVirt) {
-      if (k0 + kVirt < n) load_entries<J>(row + k0 + kVirt, en);
+    const int p0 = lane * J;  // this lane's storage slots inside every round
+    if (n > 0) load_entries<J>(row + p0, e);
+    for (int kb = 0; kb < n; kb += kVirt) {
+      if (kb + kVirt < n) load_entries<J>(row + kb + kVirt + p0, en);
 #pragma unroll
       for (int j = 0; j < J; j++) {
-        if (k0 + j < n) {
+        if (kb + row_slot(p0 + j) < n) {  // slot -> rank: pair j of the sub-warp's lanes are consecutive neighbours
           PairGeom g = load_pair(B, pos, pi, e[j]);
           rho_term<WITH_V>(T, ti, g, acc.a[j][0], acc.a[j][1], oob);
         }
@@ -208,13 +209,13 @@ namespace ofly {
     const double Fi = pi.w;
     VirtSum<G, 3> acc;
     uint32_t e[J], en[J];  // entries one round ahead (see eam_rho_atom)
-    int k0 = lane * J;
-    if (k0 < n) load_entries<J>(row + k0, e);
-    for (; k0 < n; k0 += kVirt) {
-      if (k0 + kVirt < n) load_entries<J>(row + k0 + kVirt, en);
+    const int p0 = lane * J;
+    if (n > 0) load_entries<J>(row + p0, e);
+    for (int kb = 0; kb < n; kb += kVirt) {
+      if (kb + kVirt < n) load_entries<J>(row + kb + kVirt + p0, en);
 #pragma unroll
       for (int j = 0; j < J; j++) {
-        if (k0 + j < n) {
+        if (kb + row_slot(p0 + j) < n) {
           PairGeom g = load_pair(B, pos, pi, e[j]);
           force_term(T, ti, Fi, g, acc.a[j][0], acc.a[j][1], acc.a[j][2], oob);
         }

@@ -40,7 +40,7 @@ namespace ofly {
     bool oob = false;
     double rho = 0, mx = 0, my = 0, mz = 0;
     for (int k = lane; k < n; k += G) {
-      PairGeom p = load_pair(B, pos, pi, row[k]);
+      PairGeom p = load_pair(B, pos, pi, row[row_slot(k)]);
       if (p.r2 < T.r_cut_sq) {
         double rinv = fast_rsqrt(p.r2);
         double rr = p.r2 * rinv;
@@ -112,7 +112,7 @@ namespace ofly {
       for (int b = 0; b < 3; b++) D[a][b] = Fpp_z * mu_z[a] * mu_z[b];
 
     for (int k = 0; k < n_z; k++) {
-      PairGeom p = load_pair(B, pos, pz, row_z[k]);
+      PairGeom p = load_pair(B, pos, pz, row_z[row_slot(k)]);
       if (!(p.r2 < T.r_cut_sq)) continue;  // warp-uniform
       const int a = p.j, ta = p.tj;
       double rinv = fast_rsqrt(p.r2);
@@ -165,7 +165,7 @@ namespace ofly {
         double mag = 0;
         double dag[3] = {0, 0, 0};
         if (q < n_a) {
-          PairGeom pg = load_pair(B, pos, pa_real, row_a[q]);
+          PairGeom pg = load_pair(B, pos, pa_real, row_a[row_slot(q)]);
           if (pg.r2 < T.r_cut_sq) {
             g = pg.j;
             take = (g > z && !B.frozen[g]);

@@ -81,7 +81,7 @@ struct ofly_search_graph {
   std::vector<char> key;  // bytes of everything the captured launches depend on
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  cudaGraphConditionalHandle cond_while{}, cond_if{};
+  cudaGraphConditionalHandle cond_while{}, cond_if[8] = {};  // one IF handle per tick of the WHILE body
   bool nested = false;
   void reset() {
     if (exec) cudaGraphExecDestroy(exec);

@@ -220,7 +220,7 @@ namespace ofly {
         int j = 0;
         double dx = 0, dy = 0, dz = 0, r2 = 0;
         if (k < n) {
-          const uint32_t e = row[k];
+          const uint32_t e = row[row_slot(k)];
           j = (int)(e & kIdxMask);
           const int code = (int)((e >> 24) & 31u);
           const double4 pj = pos[j];
@@ -263,7 +263,7 @@ namespace ofly {
         int j = 0;
         double dx = 0, dy = 0, dz = 0, r2 = 0;
         if (k < n) {
-          const uint32_t e = row[k];
+          const uint32_t e = row[row_slot(k)];
           j = (int)(e & kIdxMask);
           const int code = (int)((e >> 24) & 31u);
           const double4 pj = pos[j];
@@ -302,7 +302,7 @@ namespace ofly {
       const int n = B.cnt[centre];
       const double4 pc = pos[centre];
       for (int k = threadIdx.x; k < n; k += kMechThreads) {
-        const uint32_t e = row[k];
+        const uint32_t e = row[row_slot(k)];
         const int j = (int)(e & kIdxMask), code = (int)((e >> 24) & 31u);
         const double4 pj = pos[j];
         const double dx = (pj.x + shift_of(code % 3, B.box.L[0])) - pc.x, dy = (pj.y + shift_of((code / 3) % 3, B.box.L[1])) - pc.y,

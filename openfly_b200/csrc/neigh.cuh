@@ -10,16 +10,21 @@
 //                    ghosts produce) is binned with HyperGrid::cell_idx into a histogram.
 //   2. scan          exclusive scan of the histogram per replica.
 //   3. scatter       each image is written to a slot of its cell as (j | shift code << 24).
-//   4. sort_cells    the few items of a cell are sorted (slot order from atomics is arbitrary, sorting
-//                    makes the final neighbour order -- and so every later sum -- deterministic) and
-//                    the image positions x_j + s*L are written in cell order, one 32 B record each.
+//   4. sort_cells    the image positions x_j + s*L are written in cell order, one 32 B record each (the slot
+//                    order left by the atomics is arbitrary: step 6 makes the neighbour order -- and so every
+//                    later sum -- deterministic).
 //   5. build         a sub-warp per atom walks the 3x3 rows of adjacent cells (contiguous slots),
 //                    tests (pos_i - pos_n)^2 < r_list^2 in the reference's operation order with
 //                    round-to-nearest intrinsics (bit-exact neighbour sets), and compacts the hits
 //                    into the atom's row with warp ballots.
+//   6. order_rows    a warp per row sorts it by (neighbour index, shift) and stores it in the transposed
+//                    round layout of row_slot (device_common.cuh): the record gathers of the EAM passes
+//                    then fall into a few 128 B lines per load instruction.
 // All functions are written against one replica so that both the grid-wide kernels below and the
 // persistent search kernel (search.cuh) can call them.
 #pragma once
+
+#include <type_traits>
 
 #include "device_common.cuh"
 
@@ -78,20 +83,26 @@ namespace ofly {
     });
   }
 
-  // Step 4 for cell c: insertion sort of its items, then image positions in slot order.
+  constexpr int kRowSortCap = 512;  // entries one warp sorts (step 6); a longer row (no EAM list has one) keeps the build order
+
+  // Step 4 for cell c: image positions in slot order. The slot order left by the atomics of step 3 is arbitrary; it only
+  // decides the order in which step 5 finds an atom's neighbours, and step 6 sorts every row it can hold, so the cell's
+  // items are sorted here (insertion sort) only when rows may be too long for step 6.
   __device__ __forceinline__ void nb_sort_cell(const BatchDev &B, int r, int c) {
     const int *start = B.cell_start + (size_t)r * (B.grid.ncells + 1);
     long s = start[c], e = start[c + 1];
     if (e > B.img_cap) e = B.img_cap;
     uint32_t *items = B.cell_items + (size_t)r * B.img_cap;
-    for (long a = s + 1; a < e; a++) {
-      uint32_t v = items[a];
-      long b = a - 1;
-      while (b >= s && items[b] > v) {
-        items[b + 1] = items[b];
-        b--;
+    if (B.K > kRowSortCap) {
+      for (long a = s + 1; a < e; a++) {
+        uint32_t v = items[a];
+        long b = a - 1;
+        while (b >= s && items[b] > v) {
+          items[b + 1] = items[b];
+          b--;
+        }
+        items[b + 1] = v;
       }
-      items[b + 1] = v;
     }
     double4 *img = B.img_pos + (size_t)r * B.img_cap;
     const double4 *pos = B.pos4 + (size_t)r * B.N;
@@ -290,6 +301,151 @@ namespace ofly {
       nb_build_tiles<8>(B, S);
     } else {
       nb_build_tiles<16>(B, S);
+    }
+  }
+
+  // Step 6: every row of the selected replicas ordered by (neighbour index, shift code) and stored in the transposed
+  // round layout (row_slot). One warp per row: bitonic sort of the row, padded to a power of two, in shared memory.
+  // WITH16: the tile path's rows of 16-bit window slots (tile.cuh) are carried along as values.
+  // Rows of up to 32 E entries in registers: element p = 32 e + lane, bitonic network with shuffles below 32 and
+  // register pairs above. Returns with v[e] = the key of rank 32 e + lane.
+  template <int E>
+  __device__ __forceinline__ void warp_bitonic(uint32_t (&v)[E], int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * E; k2 <<= 1) {
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {  // partner in the same thread; the direction depends on e alone
+#pragma unroll
+          for (int e = 0; e < E; e++) {
+            const int f = e | (j >> 5);
+            if (f != e) {
+              const bool up = ((32 * e) & k2) == 0;
+              const uint32_t lo = min(v[e], v[f]), hi = max(v[e], v[f]);
+              v[e] = up ? lo : hi, v[f] = up ? hi : lo;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; e++) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
+            const bool up = (((32 * e) | lane) & k2) == 0, lower = (lane & j) == 0;
+            v[e] = (up == lower) ? min(v[e], o) : max(v[e], o);
+          }
+        }
+      }
+    }
+  }
+  template <int E>
+  __device__ __forceinline__ void order_row_regs(uint32_t *row, int n, int padded, int lane) {
+    uint32_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const int p = 32 * e + lane;
+      v[e] = 0xffffffffu;
+      if (p < n) {
+        const uint32_t x = row[p];
+        v[e] = (x << 8) | (x >> 24);  // index in the high 24 bits, then type and shift code
+      }
+    }
+    warp_bitonic<E>(v, lane);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const int k = 32 * e + lane;
+      if (k < padded) row[row_slot(k)] = (v[e] >> 8) | (v[e] << 24);
+    }
+  }
+
+  template <bool WITH16>
+  static __global__ void __launch_bounds__(256) k_nb_order_rows(BatchDev B, Sel S) {
+    using Key = typename std::conditional<WITH16, unsigned long long, uint32_t>::type;
+    __shared__ Key buf[8][kRowSortCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Key *key = buf[warp];
+    const long rows = (long)(*S.count) * B.N;
+    for (long w = blockIdx.x * 8L + warp; w < rows; w += gridDim.x * 8L) {
+      const int r = S.list[w / B.N], i = (int)(w % B.N);
+      const size_t at = (size_t)r * B.N + i;
+      uint32_t *row = B.nbr + at * B.K;
+      uint16_t *row16 = WITH16 ? B.tile.nbr16 + at * B.K : nullptr;
+      const int n = B.cnt[at];
+      const int padded = (n + 15) & ~15;  // K is a multiple of 16
+      if constexpr (!WITH16) {
+        if (n <= 128) {  // warp-uniform: the usual case, sorted in registers
+          if (n <= 32) {
+            order_row_regs<1>(row, n, padded, lane);
+          } else if (n <= 64) {
+            order_row_regs<2>(row, n, padded, lane);
+          } else {
+            order_row_regs<4>(row, n, padded, lane);
+          }
+          continue;
+        }
+      }
+      if (n > kRowSortCap) {              // layout only, two rounds at a time
+        for (int base = 0; base < padded; base += 32) {
+          const int k = base + lane;
+          uint32_t e = 0;
+          uint16_t e16 = 0;
+          if (k < padded) {
+            e = row[k];
+            if (WITH16) e16 = row16[k];
+          }
+          __syncwarp();
+          if (k < padded) {
+            row[row_slot(k)] = e;
+            if (WITH16) row16[row_slot(k)] = e16;
+          }
+        }
+        continue;
+      }
+      int P = 16;
+      while (P < n) P <<= 1;
+      for (int p = lane; p < P; p += 32) {
+        Key v = ~Key(0);
+        if (p < n) {
+          const uint32_t e = row[p];
+          const uint32_t rot = (e << 8) | (e >> 24);  // index in the high 24 bits, then type and shift code
+          if constexpr (WITH16) {
+            v = ((Key)rot << 16) | (Key)row16[p];
+          } else {
+            v = rot;
+          }
+        }
+        key[p] = v;
+      }
+      __syncwarp();
+      for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+          for (int t = lane; t < P / 2; t += 32) {
+            const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1)), b = a | j;
+            const Key x = key[a], y = key[b];
+            const bool up = (a & k2) == 0;
+            if ((x > y) == up) key[a] = y, key[b] = x;
+          }
+          __syncwarp();
+        }
+      }
+      for (int k = lane; k < padded; k += 32) {
+        const Key v = key[k];
+        uint32_t rot;
+        if constexpr (WITH16) {
+          rot = (uint32_t)(v >> 16);
+          row16[row_slot(k)] = (uint16_t)v;
+        } else {
+          rot = v;
+        }
+        row[row_slot(k)] = (rot >> 8) | (rot << 24);
+      }
+      __syncwarp();  // the buffer is refilled by the next row
+    }
+  }
+  // blocks: a grid-stride launch over rows_of_work rows, eight rows per CTA
+  static inline void launch_order_rows(const BatchDev &B, Sel sel, unsigned blocks, cudaStream_t st) {
+    if (B.tile.n_tiles > 0) {
+      k_nb_order_rows<true><<<blocks, 256, 0, st>>>(B, sel);
+    } else {
+      k_nb_order_rows<false><<<blocks, 256, 0, st>>>(B, sel);
     }
   }
 

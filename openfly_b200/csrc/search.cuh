@@ -13,7 +13,7 @@
 // 2-16 CTAs per entry of the list of active replicas; replicas may be at completely different places
 // of the algorithm), then ONE set of grid kernels (neigh.cuh / eam.cuh) rebuilds the lists of the
 // replicas that asked for it and evaluates the gradient of all active replicas with the whole chip.
-// A tick is a fixed sequence of kernel nodes (segment, five rebuild kernels behind an IF node that is
+// A tick is a fixed sequence of kernel nodes (segment, six rebuild kernels behind an IF node that is
 // only armed when somebody asked, two pair kernels); the host enqueues it as a CUDA graph whose body
 // repeats on the device (WHILE conditional node) until no replica is active -- no per-step host round
 // trip, no host-side branch. Finished replicas drop out of the list, so the chip stays as full as the
@@ -1245,7 +1245,7 @@ namespace ofly {
         }
         if (lane == 0) {
           P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;
-          P.ctl->kernels += 3 + ((!P.use_cond_rebuild || nr > 0) ? 5 : 0);
+          P.ctl->kernels += 3 + ((!P.use_cond_rebuild || nr > 0) ? 6 : 0);
           __threadfence();
           if (P.use_cond) cudaGraphSetConditional(P.cond, (na > P.exit_below && tick <= P.max_ticks) ? 1u : 0u);
           if (P.use_cond_rebuild) cudaGraphSetConditional(P.cond_rebuild, nr > 0 ? 1u : 0u);

@@ -40,6 +40,7 @@ namespace ofly {
     }
 
     constexpr int kSegMaxThreads = 512;
+    constexpr int kMaxTickUnroll = 8;   // ticks per pass of the device-side loop's body (tick_unroll)
     constexpr int kHostLoopTicks = 8;   // ticks between host checks when the device-side loop is off
 
     int env_int(char const *name, int dflt) {
@@ -100,6 +101,8 @@ namespace ofly {
       }
       int ft = env_int("OFLY_TEAM_THREADS", 0);  // tuning overrides
       if (ft == 128 || ft == 256 || ft == 512) t.threads = ft, t.cluster = 1;
+      int st = env_int("OFLY_SEG_THREADS", 0);  // narrower CTAs of the same cluster: two CTAs per SM
+      if ((st == 128 || st == 256) && st < t.threads) t.threads = st;
       int forced = env_int("OFLY_CLUSTER", 0);
       if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) t.cluster = forced;
       // step down while the device cannot co-schedule one cluster of this size (the team width is a property of the
@@ -194,6 +197,7 @@ namespace ofly {
       if (B.tile.n_tiles > 0) {  // cell-tiled build (tile.cuh): same rows, candidates tested from shared memory
         OFLY_CUDA(tile_prepare());
         tile_launch_build(B, reb, stride_grid(ctx, (size_t)cap * (size_t)B.tile.n_tiles, env_int("OFLY_TILE_CTAS", 12)), st);
+        launch_order_rows(B, reb, stride_grid(ctx, (atoms + 7) / 8, 8), st);
         OFLY_CUDA(cudaGetLastError());
         return;
       }
@@ -212,6 +216,7 @@ namespace ofly {
           k_nb_build_dyn<<<pg.blocks, 256, 0, st>>>(B, reb, 4 * pg.slots);  // budget: four waves of resident threads
           break;
       }
+      launch_order_rows(B, reb, stride_grid(ctx, (atoms + 7) / 8, 8), st);
       OFLY_CUDA(cudaGetLastError());
     }
 
@@ -274,6 +279,11 @@ namespace ofly {
       }
     };
 
+    // Ticks per pass of the WHILE body. The loop-back of a conditional node costs about as much as two kernel boundaries
+    // (9 us of a 72 us tick with one small replica left, profiles/r3h_tick_anatomy_*): a body of several ticks pays it once.
+    // The ticks after the one that ends the loop find an empty list and leave at once.
+    int tick_unroll() { return std::max(1, std::min(kMaxTickUnroll, env_int("OFLY_TICK_UNROLL", 4))); }
+
     // Everything a captured tick depends on: the kernels' by-value arguments, the launch shapes and the graph's form.
     std::vector<char> graph_key(ofly_batch *b, SearchParams const &P, TeamShape shape, bool nested, long cap) {
       const PairGrid pg = pair_grid(b, cap);
@@ -281,11 +291,13 @@ namespace ofly {
       auto put = [&k](const void *p, size_t n) { k.insert(k.end(), (const char *)p, (const char *)p + n); };
       put(&P, sizeof P), put(&b->d, sizeof b->d), put(&b->tables->dev, sizeof b->tables->dev);
       put(&shape, sizeof shape), put(&pg, sizeof pg), put(&nested, sizeof nested), put(&cap, sizeof cap);
+      const int unroll = tick_unroll();
+      put(&unroll, sizeof unroll);
       return k;
     }
 
     // The whole search as ONE graph launch: a WHILE conditional node whose body is one tick; the segment
-    // kernel clears the condition when no replica is active. With `nested` the five rebuild kernels sit in
+    // kernel clears the condition when no replica is active. With `nested` the six rebuild kernels sit in
     // an IF node inside the body that the segment kernel arms only when some replica asked for a rebuild
     // (late in a batch most ticks have none, and five empty launches are a sixth of such a tick).
     // The instantiated graph is kept in the batch and reused while the key above is unchanged (a Master calls with the
@@ -311,39 +323,46 @@ namespace ofly {
           OFLY_CUDA(cudaGraphAddNode(&node, g.graph, nullptr, 0, &np));
           cudaGraph_t body = np.conditional.phGraph_out[0];
           P.use_cond = 1, P.cond = g.cond_while;
-          cudaGraph_t if_body = nullptr;
-          if (nested) {
-            OFLY_CUDA(cudaGraphConditionalHandleCreate(&g.cond_if, g.graph, 0, cudaGraphCondAssignDefault));
-            P.use_cond_rebuild = 1, P.cond_rebuild = g.cond_if;
+          const int unroll = tick_unroll();
+          cudaGraph_t if_body[kMaxTickUnroll] = {};
+          SearchParams Pu[kMaxTickUnroll];
+          for (int u = 0; u < unroll; u++) {
+            Pu[u] = P;
+            if (nested) {  // a handle belongs to one conditional node: one per tick of the body
+              OFLY_CUDA(cudaGraphConditionalHandleCreate(&g.cond_if[u], g.graph, 0, cudaGraphCondAssignDefault));
+              Pu[u].use_cond_rebuild = 1, Pu[u].cond_rebuild = g.cond_if[u];
+            }
           }
           {
             OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
             CaptureScope cap(ctx->stream);
-            enqueue_segment(b, P, shape, grid_cap);
-            if (nested) {
-              cudaStreamCaptureStatus status;
-              const cudaGraphNode_t *deps = nullptr;
-              size_t n_deps = 0;
-              OFLY_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, nullptr, &deps, &n_deps));
-              cudaGraphNodeParams ip{};
-              ip.type = cudaGraphNodeTypeConditional;
-              ip.conditional.handle = g.cond_if;
-              ip.conditional.type = cudaGraphCondTypeIf;
-              ip.conditional.size = 1;
-              cudaGraphNode_t if_node;
-              OFLY_CUDA(cudaGraphAddNode(&if_node, body, deps, n_deps, &ip));
-              if_body = ip.conditional.phGraph_out[0];
-              OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
-            } else {
-              enqueue_rebuild(b, P, grid_cap);
+            for (int u = 0; u < unroll; u++) {
+              enqueue_segment(b, Pu[u], shape, grid_cap);
+              if (nested) {
+                cudaStreamCaptureStatus status;
+                const cudaGraphNode_t *deps = nullptr;
+                size_t n_deps = 0;
+                OFLY_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, nullptr, &deps, &n_deps));
+                cudaGraphNodeParams ip{};
+                ip.type = cudaGraphNodeTypeConditional;
+                ip.conditional.handle = g.cond_if[u];
+                ip.conditional.type = cudaGraphCondTypeIf;
+                ip.conditional.size = 1;
+                cudaGraphNode_t if_node;
+                OFLY_CUDA(cudaGraphAddNode(&if_node, body, deps, n_deps, &ip));
+                if_body[u] = ip.conditional.phGraph_out[0];
+                OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
+              } else {
+                enqueue_rebuild(b, Pu[u], grid_cap);
+              }
+              enqueue_gradient(b, Pu[u], grid_cap);
             }
-            enqueue_gradient(b, P, grid_cap);
             cap.end();
           }
-          if (nested) {
-            OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, if_body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+          for (int u = 0; nested && u < unroll; u++) {
+            OFLY_CUDA(cudaStreamBeginCaptureToGraph(ctx->stream, if_body[u], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
             CaptureScope cap(ctx->stream);
-            enqueue_rebuild(b, P, grid_cap);
+            enqueue_rebuild(b, Pu[u], grid_cap);
             cap.end();
           }
           OFLY_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));

@@ -250,12 +250,12 @@ namespace ofly {
         bool oob = false;
         if constexpr (!FORCE) {
           VirtSum<G, 2> acc;
-          for (int k0 = lane * J; k0 < n; k0 += kVirt) {
+          for (int kb = 0; kb < n; kb += kVirt) {
             uint32_t e[J];
-            load_entries16<J>(row + k0, e);
+            load_entries16<J>(row + kb + lane * J, e);
 #pragma unroll
             for (int j = 0; j < J; j++) {
-              if (k0 + j < n) rho_term<false>(T, ti, tile_pair(S, (int)e[j], pi), acc.a[j][0], acc.a[j][1], oob);
+              if (kb + row_slot(lane * J + j) < n) rho_term<false>(T, ti, tile_pair(S, (int)e[j], pi), acc.a[j][0], acc.a[j][1], oob);
             }
           }
           double tot[2];
@@ -266,12 +266,12 @@ namespace ofly {
           if (!B.frozen[i]) {
             const double Fi = pi.w;
             VirtSum<G, 3> acc;
-            for (int k0 = lane * J; k0 < n; k0 += kVirt) {
+            for (int kb = 0; kb < n; kb += kVirt) {
               uint32_t e[J];
-              load_entries16<J>(row + k0, e);
+              load_entries16<J>(row + kb + lane * J, e);
 #pragma unroll
               for (int j = 0; j < J; j++) {
-                if (k0 + j < n) force_term(T, ti, Fi, tile_pair(S, (int)e[j], pi), acc.a[j][0], acc.a[j][1], acc.a[j][2], oob);
+                if (kb + row_slot(lane * J + j) < n) force_term(T, ti, Fi, tile_pair(S, (int)e[j], pi), acc.a[j][0], acc.a[j][1], acc.a[j][2], oob);
               }
             }
             acc.total(tot);

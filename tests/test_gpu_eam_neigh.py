@@ -226,6 +226,35 @@ def test_sums_do_not_depend_on_subwarp_width(gpu):
     s1.close()
 
 
+def test_rows_are_ordered_by_neighbour_index(gpu):
+    """Step 6 of the rebuild (neigh.cuh, k_nb_order_rows): every stored row is ordered by (neighbour index, image shift)
+    whatever slot order the atomics of the cell binning produced, so two rebuilds from the same positions give the same
+    rows, and gradients computed on them the same bits; rows of every length class (<= 32, <= 64, <= 128 entries sorted in
+    registers, longer ones in shared memory) take it."""
+    fly, ctx, data = gpu
+    pot = fly.Generic(data)
+    for n, extra, lo, hi in ((5, 0.17, 33, 64), (6, -1.2, 1, 32), (6, 1.2, 65, 128), (6, 2.0, 129, 512)):
+        pos, ex, ids = bcc_vacancy(n, a=2.855, remove=(1,), jitter=0.05, hydrogen=True)
+        s = fly.System(data, fly.Box(tuple(ex)), ids, replicas=2)
+        nl = fly.List(s, data.rcut() + extra)
+        P = np.stack([pos, pos + 0.01])
+        seen = []
+        for _ in range(2):
+            nl.rebuild(P)
+            cnt, idx, sh = nl.export(1)
+            off = np.concatenate([[0], np.cumsum(cnt)])
+            key = idx.astype(np.int64) * 32 + sh
+            for i in range(len(cnt)):
+                row = key[off[i]:off[i + 1]]
+                assert (np.diff(row) > 0).all(), f"row {i} is not strictly ordered"
+            seen.append((cnt, idx, sh, pot.gradient(nl) if extra > 0 else None))
+        assert all(np.array_equal(x, y) for x, y in zip(seen[0][:3], seen[1][:3]))
+        if extra > 0:
+            assert np.array_equal(seen[0][3], seen[1][3])
+        assert lo <= np.median(cnt) <= hi, (np.median(cnt), lo, hi)
+        s.close()
+
+
 def test_tables_from_memory_and_from_knots(gpu):
     """DataEAM(std::istream) (data.cpp:67) and tables handed over as knots: same bits as the path constructor; EAM's
     TypeMap check (eam.hpp:50-63)."""
