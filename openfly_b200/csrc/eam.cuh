@@ -261,8 +261,11 @@ namespace ofly {
       if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
   }
+#ifndef OFLY_RHO_MINB
+#define OFLY_RHO_MINB 1
+#endif
   template <int G>
-  static __global__ void __launch_bounds__(256) k_eam_rho(BatchDev B, TablesDev T, Sel S) {
+  static __global__ void __launch_bounds__(256, OFLY_RHO_MINB) k_eam_rho(BatchDev B, TablesDev T, Sel S) {
     eam_rho_tiles<G>(B, T, S);
   }
 
@@ -322,7 +325,7 @@ namespace ofly {
     }
   }
 
-  static __global__ void __launch_bounds__(256) k_eam_rho_dyn(BatchDev B, TablesDev T, Sel S, long slots, unsigned long long *trace, int trace_cap) {
+  static __global__ void __launch_bounds__(256, OFLY_RHO_MINB) k_eam_rho_dyn(BatchDev B, TablesDev T, Sel S, long slots, unsigned long long *trace, int trace_cap) {
     kernel_stamp(trace, trace_cap, 91);
     switch (group_for((long)(*S.count) * B.N, slots)) {
       case 4: eam_rho_tiles<4>(B, T, S); break;

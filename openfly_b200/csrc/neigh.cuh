@@ -24,6 +24,8 @@
 // persistent search kernel (search.cuh) can call them.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include <type_traits>
 
 #include "device_common.cuh"
@@ -357,11 +359,14 @@ namespace ofly {
   }
 
   template <bool WITH16>
-  static __global__ void __launch_bounds__(256) k_nb_order_rows(BatchDev B, Sel S) {
-    using Key = typename std::conditional<WITH16, unsigned long long, uint32_t>::type;
-    __shared__ Key buf[8][kRowSortCap];
+  using RowSortKey = typename std::conditional<WITH16, unsigned long long, uint32_t>::type;
+
+  // buf: kRowSortCap keys per warp of the (256-thread) CTA
+  template <bool WITH16>
+  __device__ __forceinline__ void nb_order_rows(const BatchDev &B, const Sel &S, RowSortKey<WITH16> *buf) {
+    using Key = RowSortKey<WITH16>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Key *key = buf[warp];
+    Key *key = buf + (size_t)warp * kRowSortCap;
     const long rows = (long)(*S.count) * B.N;
     for (long w = blockIdx.x * 8L + warp; w < rows; w += gridDim.x * 8L) {
       const int r = S.list[w / B.N], i = (int)(w % B.N);
@@ -440,6 +445,11 @@ namespace ofly {
       __syncwarp();  // the buffer is refilled by the next row
     }
   }
+  template <bool WITH16>
+  static __global__ void __launch_bounds__(256) k_nb_order_rows(BatchDev B, Sel S) {
+    __shared__ RowSortKey<WITH16> buf[8 * kRowSortCap];
+    nb_order_rows<WITH16>(B, S, buf);
+  }
   // blocks: a grid-stride launch over rows_of_work rows, eight rows per CTA
   static inline void launch_order_rows(const BatchDev &B, Sel sel, unsigned blocks, cudaStream_t st) {
     if (B.tile.n_tiles > 0) {
@@ -447,6 +457,42 @@ namespace ofly {
     } else {
       k_nb_order_rows<false><<<blocks, 256, 0, st>>>(B, sel);
     }
+  }
+
+  // Steps 1-6 for the selected replicas in ONE cooperative launch, grid-wide barriers between the steps. Inside a search
+  // most ticks have nobody to rebuild: this kernel then costs one empty launch, where six separate kernels behind an IF
+  // node cost the evaluation of the conditional node (~10 us of a ~70 us tick late in a batch, profiles/). Same rows as
+  // the separate kernels. The grid must be co-resident (cooperative launch); every loop is a grid-stride loop.
+  static __global__ void __launch_bounds__(256) k_nb_rebuild_fused(BatchDev B, Sel S, const double *__restrict__ pos, size_t stride, long budget) {
+    const int nsel = *S.count;
+    if (nsel == 0) return;  // the whole grid leaves
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ uint32_t buf[8 * kRowSortCap];
+    const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t atoms = (size_t)nsel * B.N;
+    for (size_t t = gtid; t < atoms; t += gthreads) {
+      const int r = S.list[t / B.N];
+      nb_canon_count(B, pos + (size_t)r * stride, r, (int)(t % B.N));
+    }
+    grid.sync();
+    for (int a = blockIdx.x; a < nsel; a += gridDim.x) nb_scan_block(B, S.list[a], reinterpret_cast<int *>(buf));
+    grid.sync();
+    for (size_t t = gtid; t < atoms; t += gthreads) nb_scatter(B, S.list[t / B.N], (int)(t % B.N));
+    grid.sync();
+    const size_t cells = (size_t)nsel * B.grid.ncells;
+    for (size_t t = gtid; t < cells; t += gthreads) nb_sort_cell(B, S.list[t / B.grid.ncells], (int)(t % B.grid.ncells));
+    grid.sync();
+    if ((long)atoms * 32 <= budget) {  // widths as k_nb_build_dyn
+      nb_build_tiles<32>(B, S);
+    } else if ((long)atoms * 16 <= budget) {
+      nb_build_tiles<16>(B, S);
+    } else if ((long)atoms * 8 <= budget) {
+      nb_build_tiles<8>(B, S);
+    } else {
+      nb_build_tiles<16>(B, S);
+    }
+    grid.sync();
+    nb_order_rows<false>(B, S, buf);
   }
 
   static __global__ void __launch_bounds__(256) k_nb_update(BatchDev B, const double *__restrict__ delta) {

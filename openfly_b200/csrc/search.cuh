@@ -117,6 +117,7 @@ namespace ofly {
     int trace_replica, trace_cap;
     int gram;  // 1: single-pass L-BFGS step (newton_step_gram), 0: pass-per-pair two-loop (newton_step)
     cudaGraphConditionalHandle cond;
+    int fused_rebuild;     // the rebuild of a tick is ONE cooperative kernel (k_nb_rebuild_fused) instead of six behind an IF node
     int use_cond_rebuild;  // the rebuild kernels of a tick sit in an IF node that is skipped when nobody asked
     cudaGraphConditionalHandle cond_rebuild;
   };
@@ -1245,7 +1246,7 @@ namespace ofly {
         }
         if (lane == 0) {
           P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;
-          P.ctl->kernels += 3 + ((!P.use_cond_rebuild || nr > 0) ? 6 : 0);
+          P.ctl->kernels += 3 + (P.fused_rebuild ? 1 : ((!P.use_cond_rebuild || nr > 0) ? 6 : 0));
           __threadfence();
           if (P.use_cond) cudaGraphSetConditional(P.cond, (na > P.exit_below && tick <= P.max_ticks) ? 1u : 0u);
           if (P.use_cond_rebuild) cudaGraphSetConditional(P.cond_rebuild, nr > 0 ? 1u : 0u);

@@ -220,6 +220,39 @@ namespace ofly {
       OFLY_CUDA(cudaGetLastError());
     }
 
+    // Co-resident CTAs of the fused rebuild kernel on this device (0: cooperative launch unavailable).
+    int fused_rebuild_blocks(ofly_ctx *ctx) {
+      static std::map<int, int> known;
+      static std::mutex known_mutex;
+      std::lock_guard<std::mutex> lock(known_mutex);
+      auto it = known.find(ctx->device);
+      if (it != known.end()) return it->second;
+      int coop = 0, per_sm = 0;
+      if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) != cudaSuccess) cudaGetLastError(), coop = 0;
+      if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nb_rebuild_fused, 256, 0) != cudaSuccess) cudaGetLastError(), per_sm = 0;
+      return known[ctx->device] = coop ? per_sm * ctx->sm_count : 0;
+    }
+
+    // The rebuild of a tick as one cooperative kernel (neigh.cuh, k_nb_rebuild_fused): row kernels only.
+    void enqueue_rebuild_fused(ofly_batch *b, SearchParams const &P, long cap) {
+      ofly_ctx *ctx = b->ctx;
+      BatchDev const &B = b->d;
+      Sel reb{P.rebuild, &P.ctl->n_rebuild};
+      const long slots = (long)ctx->sm_count * 2048;
+      const size_t want = ((size_t)cap * b->N * 32 + 255) / 256;  // a 32-lane group per atom
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)fused_rebuild_blocks(ctx))));
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr, cfg.numAttrs = 1;
+      const double *pos = P.ws;
+      OFLY_CUDA(cudaLaunchKernelEx(&cfg, k_nb_rebuild_fused, B, reb, pos, P.ws_stride, 4 * slots));
+    }
+
     void enqueue_gradient(ofly_batch *b, SearchParams const &P, long cap) {
       cudaStream_t st = b->ctx->stream;
       BatchDev const &B = b->d;
@@ -285,14 +318,14 @@ namespace ofly {
     int tick_unroll() { return std::max(1, std::min(kMaxTickUnroll, env_int("OFLY_TICK_UNROLL", 4))); }
 
     // Everything a captured tick depends on: the kernels' by-value arguments, the launch shapes and the graph's form.
-    std::vector<char> graph_key(ofly_batch *b, SearchParams const &P, TeamShape shape, bool nested, long cap) {
+    std::vector<char> graph_key(ofly_batch *b, SearchParams const &P, TeamShape shape, bool nested, bool fused, long cap) {
       const PairGrid pg = pair_grid(b, cap);
       std::vector<char> k;
       auto put = [&k](const void *p, size_t n) { k.insert(k.end(), (const char *)p, (const char *)p + n); };
       put(&P, sizeof P), put(&b->d, sizeof b->d), put(&b->tables->dev, sizeof b->tables->dev);
       put(&shape, sizeof shape), put(&pg, sizeof pg), put(&nested, sizeof nested), put(&cap, sizeof cap);
       const int unroll = tick_unroll();
-      put(&unroll, sizeof unroll);
+      put(&unroll, sizeof unroll), put(&fused, sizeof fused);
       return k;
     }
 
@@ -303,11 +336,12 @@ namespace ofly {
     // The instantiated graph is kept in the batch and reused while the key above is unchanged (a Master calls with the
     // same buffers batch after batch); the conditional handles are part of the kernels' arguments, so they are kept too.
     // Returns false if the graph could not be constructed (nothing was launched).
-    bool try_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, bool nested, long grid_cap, int level) {
+    bool try_device_loop(ofly_batch *b, SearchParams P, TeamShape shape, bool nested, bool fused, long grid_cap, int level) {
       ofly_ctx *ctx = b->ctx;
       ofly_search_graph &g = b->search_graph[level];
       P.use_cond = 0, P.use_cond_rebuild = 0, P.cond = cudaGraphConditionalHandle{}, P.cond_rebuild = cudaGraphConditionalHandle{};
-      std::vector<char> key = graph_key(b, P, shape, nested, grid_cap);
+      P.fused_rebuild = fused ? 1 : 0;
+      std::vector<char> key = graph_key(b, P, shape, nested, fused, grid_cap);
       const bool reuse = g.exec != nullptr && g.key == key && !std::getenv("OFLY_NO_GRAPH_CACHE");
       if (!reuse) {
         g.reset();
@@ -352,6 +386,8 @@ namespace ofly {
                 OFLY_CUDA(cudaGraphAddNode(&if_node, body, deps, n_deps, &ip));
                 if_body[u] = ip.conditional.phGraph_out[0];
                 OFLY_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &if_node, 1, cudaStreamSetCaptureDependencies));
+              } else if (fused) {
+                enqueue_rebuild_fused(b, Pu[u], grid_cap);
               } else {
                 enqueue_rebuild(b, Pu[u], grid_cap);
               }
@@ -370,11 +406,11 @@ namespace ofly {
         } catch (Error const &e) {
           cudaGetLastError();
           g.reset();
-          if (!nested) throw;
-          if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: nested rebuild IF node unavailable (%s); flat tick graph\n", e.what());
+          if (!nested && !fused) throw;
+          if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: %s unavailable (%s); next form of the tick graph\n", fused ? "fused cooperative rebuild" : "nested rebuild IF node", e.what());
           return false;
         }
-        if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: search graph with %s rebuild\n", nested ? "IF-guarded" : "unconditional");
+        if (std::getenv("OFLY_VERBOSE")) std::fprintf(stderr, "openfly_b200: search graph with %s rebuild\n", fused ? "fused cooperative" : (nested ? "IF-guarded" : "unconditional"));
       }
       OFLY_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
       OFLY_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -390,6 +426,10 @@ namespace ofly {
       ofly_ctx *ctx = b->ctx;
       char const *v = std::getenv("OFLY_REBUILD_IF");
       bool nested = !(v && std::string(v) == "0");
+      // one cooperative rebuild kernel instead of the IF node: opt-in (OFLY_REBUILD_FUSED=1, row kernels only). Measured: a late
+      // tick of a 432-atom replica 71.1 -> 69.6 us, but a tick with 32 of 64 16 000-atom replicas busy 814 -> 882 us (the
+      // cooperative grid holds 4 CTAs per SM where the separate build kernel runs at its own occupancy).
+      bool fused = env_int("OFLY_REBUILD_FUSED", 0) && b->d.tile.n_tiles == 0 && fused_rebuild_blocks(ctx) > 0;
       long caps[3] = {n0, 0, 0};
       int levels = 1;
       if (env_int("OFLY_STAGES", 1)) {
@@ -399,9 +439,10 @@ namespace ofly {
       for (int L = 0; L < levels && active > 0; L++) {
         if (L + 1 < levels && active <= caps[L + 1]) continue;  // already small enough for the next stage
         P.exit_below = L + 1 < levels ? (int)caps[L + 1] : 0;
-        if (!(nested && try_device_loop(b, P, shape, true, caps[L], L))) {
+        if (fused && !try_device_loop(b, P, shape, false, true, caps[L], L)) fused = false;
+        if (!fused && !(nested && try_device_loop(b, P, shape, true, false, caps[L], L))) {
           nested = false;
-          try_device_loop(b, P, shape, false, caps[L], L);
+          try_device_loop(b, P, shape, false, false, caps[L], L);
         }
         Control c{};
         OFLY_CUDA(cudaMemcpyAsync(&c, P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
