@@ -261,8 +261,10 @@ namespace ofly {
       if (oob) atomicOr(B.fault + r, kFaultOutOfBounds);
     }
   }
+  // Pass 1 is capped for five CTAs per SM (48 registers, 32 B spilled outside the pair loop): measured 0.709 ms per launch
+  // pair of the 64 x 16 000 batch against 0.719 uncapped (60 registers, four CTAs) and 0.766 capped for six (40 registers).
 #ifndef OFLY_RHO_MINB
-#define OFLY_RHO_MINB 1
+#define OFLY_RHO_MINB 5
 #endif
   template <int G>
   static __global__ void __launch_bounds__(256, OFLY_RHO_MINB) k_eam_rho(BatchDev B, TablesDev T, Sel S) {
