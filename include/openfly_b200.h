@@ -113,7 +113,8 @@ int ofly_neigh_update(ofly_batch *b, const double *delta_host);
 int ofly_neigh_update_dev(ofly_batch *b, const double *delta_dev);
 /* Stored (unfiltered) neighbour lists of one replica as (real index, image shift code) pairs,
  * shift code = (sx+1) + 3(sy+1) + 9(sz+1). counts: [N]; idx/shift: flattened, capacity cap;
- * *total receives the number of pairs (may exceed cap, then only cap were written). */
+ * *total receives the number of pairs (may exceed cap, then only cap were written). An atom's pairs come in stored order:
+ * ascending (real index, shift code) -- the reference's own order (cell walk over its ghost array) is not reproduced, the set is. */
 int ofly_neigh_export(ofly_batch *b, long replica, int *counts_host, int *idx_host, int *shift_host, long cap, long *total);
 /* HyperGrid::cell_idx (hypergrid.hpp:75-99) of every real atom's canonical image. out: [N]. */
 int ofly_neigh_cells(ofly_batch *b, long replica, int *cell_host);
