@@ -81,6 +81,7 @@ namespace ofly {
     long long kernels;  // kernels executed so far (an IF-guarded rebuild only counts when it ran)
     int queue_head;     // next search of the queue that no slot has claimed yet
     int fault_or;       // OR of the fault bits that ended a search (slots are re-armed, their own fault words reset)
+    int if_state[3][8]; // value last given to the rebuild IF handle of tick u of the body of stage L's graph (0 at launch)
   };
 
   struct SearchParams {
@@ -117,6 +118,7 @@ namespace ofly {
     int trace_replica, trace_cap;
     int gram;  // 1: single-pass L-BFGS step (newton_step_gram), 0: pass-per-pair two-loop (newton_step)
     cudaGraphConditionalHandle cond;
+    int stage, body_slot;  // which graph (stage of the device-side loop) and which tick of its body this launch is
     int fused_rebuild;     // the rebuild of a tick is ONE cooperative kernel (k_nb_rebuild_fused) instead of six behind an IF node
     int use_cond_rebuild;  // the rebuild kernels of a tick sit in an IF node that is skipped when nobody asked
     cudaGraphConditionalHandle cond_rebuild;
@@ -330,7 +332,10 @@ namespace ofly {
   // elements per thread, each a round trip to L2/HBM), so all inputs of kPassUnroll elements are fetched
   // before the first is used. body(t, v) sees v[k] = src[k][t]; a thread visits its elements in
   // ascending t, so fused dot products accumulate in the same order whatever the unroll.
-  constexpr int kPassUnroll = 4;
+#ifndef OFLY_PASS_UNROLL
+#define OFLY_PASS_UNROLL 4
+#endif
+  constexpr int kPassUnroll = OFLY_PASS_UNROLL;
   template <int NIN, typename F>
   __device__ __forceinline__ void team_pass(int tid, int nthreads, int n, const double *const (&src)[NIN], F &&body) {
     for (int t0 = tid; t0 < n; t0 += kPassUnroll * nthreads) {
@@ -1248,8 +1253,15 @@ namespace ofly {
           P.ctl->n_active = na, P.ctl->n_rebuild = nr, P.ctl->ticket = 0, P.ctl->tick = tick;
           P.ctl->kernels += 3 + (P.fused_rebuild ? 1 : ((!P.use_cond_rebuild || nr > 0) ? 6 : 0));
           __threadfence();
-          if (P.use_cond) cudaGraphSetConditional(P.cond, (na > P.exit_below && tick <= P.max_ticks) ? 1u : 0u);
-          if (P.use_cond_rebuild) cudaGraphSetConditional(P.cond_rebuild, nr > 0 ? 1u : 0u);
+          // The device-side call that sets a conditional handle is only made when the value changes (it is a good part of
+          // the ~10 us this bookkeeping takes in a late tick): the WHILE handle is 1 at launch and only ever goes to 0, the IF
+          // handle of this tick of the body is 0 at launch and its last value is kept in the control block.
+          if (P.use_cond && !(na > P.exit_below && tick <= P.max_ticks)) cudaGraphSetConditional(P.cond, 0u);
+          if (P.use_cond_rebuild) {
+            const int want = nr > 0 ? 1 : 0;
+            int *have = &P.ctl->if_state[P.stage][P.body_slot];
+            if (want || *have) cudaGraphSetConditional(P.cond_rebuild, (unsigned)want), *have = want;  // 1 is always (re)stated
+          }
           if (P.trace != nullptr) trace_mark(P, P.trace_replica, 0, 95);  // end of the tick's bookkeeping
         }
       }

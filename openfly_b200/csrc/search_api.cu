@@ -341,6 +341,7 @@ namespace ofly {
       ofly_search_graph &g = b->search_graph[level];
       P.use_cond = 0, P.use_cond_rebuild = 0, P.cond = cudaGraphConditionalHandle{}, P.cond_rebuild = cudaGraphConditionalHandle{};
       P.fused_rebuild = fused ? 1 : 0;
+      P.stage = level, P.body_slot = 0;
       std::vector<char> key = graph_key(b, P, shape, nested, fused, grid_cap);
       const bool reuse = g.exec != nullptr && g.key == key && !std::getenv("OFLY_NO_GRAPH_CACHE");
       if (!reuse) {
@@ -362,6 +363,7 @@ namespace ofly {
           SearchParams Pu[kMaxTickUnroll];
           for (int u = 0; u < unroll; u++) {
             Pu[u] = P;
+            Pu[u].body_slot = u;
             if (nested) {  // a handle belongs to one conditional node: one per tick of the body
               OFLY_CUDA(cudaGraphConditionalHandleCreate(&g.cond_if[u], g.graph, 0, cudaGraphCondAssignDefault));
               Pu[u].use_cond_rebuild = 1, Pu[u].cond_rebuild = g.cond_if[u];
