@@ -28,6 +28,8 @@ namespace ofly {
   // index, so the 32 records one warp-wide load instruction gathers (8 consecutive atoms x 4 consecutive neighbours) sit
   // in a few 128 B lines instead of one line per lane: the L1 data pipe serves a load per distinct line.
   __host__ __device__ constexpr int row_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
+  static_assert(row_slot(0) == 0 && row_slot(1) == 4 && row_slot(4) == 1 && row_slot(7) == 13 && row_slot(15) == 15, "4 x 4 transpose of a round");
+  static_assert(row_slot(16 + 6) == 16 + 9 && row_slot(row_slot(37)) == 37 && row_slot(row_slot(100)) == 100, "rounds stay in place, the map is an involution");
 
   // Fault bits recorded per replica.
   constexpr int kFaultOutOfBounds = 1;  // Spline::OutOfBounds
