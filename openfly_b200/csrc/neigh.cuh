@@ -116,55 +116,55 @@ namespace ofly {
       double ix = sx == 1 ? p.x : (sx == 0 ? __dsub_rn(p.x, B.box.L[0]) : __dadd_rn(p.x, B.box.L[0]));
       double iy = sy == 1 ? p.y : (sy == 0 ? __dsub_rn(p.y, B.box.L[1]) : __dadd_rn(p.y, B.box.L[1]));
       double iz = sz == 1 ? p.z : (sz == 0 ? __dsub_rn(p.z, B.box.L[2]) : __dadd_rn(p.z, B.box.L[2]));
-      st256(img + a, make_double4(ix, iy, iz, __longlong_as_double((long long)v)));
+      // w = the row entry this image becomes: (index | shift code << 24 | type << 29)
+      st256(img + a, make_double4(ix, iy, iz, __longlong_as_double((long long)(v | ((uint32_t)B.type[v & kIdxMask] << 29)))));
     }
   }
 
-  // Step 5 for atom i, executed by the G lanes of one sub-warp (all G lanes must call).
+  // Step 5 for atom i, executed by the G lanes of one sub-warp (all G lanes must call). The kernel is bound by instruction
+  // issue (profiles/), so the candidate loop is branch-free: 32-bit slot indices, the record of a lane beyond the run's
+  // end is a clamped (discarded) load, the entry with its type bits comes ready-made out of the image record.
   template <int G>
   __device__ __forceinline__ void nb_build_atom(const BatchDev &B, int r, int i, int lane) {
     const int sub = ((threadIdx.x & 31) / G) * G;  // first lane of this sub-warp inside the warp
     const unsigned gmask = group_mask<G>();
+    const unsigned below = (1u << lane) - 1u;
 
-    double4 pi = ld256(B.pos4 + (size_t)r * B.N + i);
+    const double4 pi = ld256(B.pos4 + (size_t)r * B.N + i);
     const int *start = B.cell_start + (size_t)r * (B.grid.ncells + 1);
     const double4 *img = B.img_pos + (size_t)r * B.img_cap;
     uint32_t *row = B.nbr + ((size_t)r * B.N + i) * B.K;
     const uint32_t self = (uint32_t)i | ((uint32_t)kShiftCentre << 24);
     const double rl2 = B.grid.r_list_sq;
+    const int K = B.K;
+    const int cap = (int)(B.img_cap < 0x7fffffffL ? B.img_cap : 0x7fffffffL);
 
-    int c = B.cell_of[(size_t)r * B.N + i];
-    int cx = c % B.grid.shape[0], cy = (c / B.grid.shape[0]) % B.grid.shape[1], cz = c / (B.grid.shape[0] * B.grid.shape[1]);
-    int x0 = max(cx - 1, 0), x1 = min(cx + 1, B.grid.shape[0] - 1);
+    const int c = B.cell_of[(size_t)r * B.N + i];
+    const int cx = c % B.grid.shape[0], cy = (c / B.grid.shape[0]) % B.grid.shape[1], cz = c / (B.grid.shape[0] * B.grid.shape[1]);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, B.grid.shape[0] - 1);
 
     int count = 0;
     for (int oz = max(cz - 1, 0); oz <= min(cz + 1, B.grid.shape[2] - 1); oz++) {
       for (int oy = max(cy - 1, 0); oy <= min(cy + 1, B.grid.shape[1] - 1); oy++) {
-        int base = oy * B.grid.prod[1] + oz * B.grid.prod[2];
-        long s = start[base + x0], e = start[base + x1 + 1];
-        if (e > B.img_cap) e = B.img_cap;
-        for (long a0 = s; a0 < e; a0 += G) {
-          long a = a0 + lane;
-          bool hit = false;
-          uint32_t entry = 0;
-          if (a < e) {
-            double4 q = ld256(img + a);
-            entry = (uint32_t)__double_as_longlong(q.w);
-            double dx = __dsub_rn(pi.x, q.x), dy = __dsub_rn(pi.y, q.y), dz = __dsub_rn(pi.z, q.z);
-            hit = entry != self && norm_sq_rn(dx, dy, dz) < rl2;
-          }
-          unsigned b = __ballot_sync(gmask, hit) >> sub;  // sub-warps loop independently: ballot over own lanes only
-          if (hit) {
-            int k = count + __popc(b & ((1u << lane) - 1u));
-            if (k < B.K) row[k] = entry | ((uint32_t)B.type[entry & kIdxMask] << 29);
-          }
+        const int base = oy * B.grid.prod[1] + oz * B.grid.prod[2];
+        const int s = start[base + x0], e = min(start[base + x1 + 1], cap);
+        for (int a0 = s; a0 < e; a0 += G) {
+          const int a = a0 + lane;
+          const bool in = a < e;
+          const double4 q = ld256(img + (in ? a : e - 1));
+          const uint32_t entry = (uint32_t)__double_as_longlong(q.w);
+          const double dx = __dsub_rn(pi.x, q.x), dy = __dsub_rn(pi.y, q.y), dz = __dsub_rn(pi.z, q.z);
+          const bool hit = in && (entry & 0x1FFFFFFFu) != self && norm_sq_rn(dx, dy, dz) < rl2;
+          const unsigned b = __ballot_sync(gmask, hit) >> sub;  // sub-warps loop independently: ballot over own lanes only
+          const int k = count + __popc(b & below);
+          if (hit && k < K) row[k] = entry;
           count += __popc(b);
         }
       }
     }
     if (lane == 0) {
-      B.cnt[(size_t)r * B.N + i] = min(count, B.K);
-      if (count > B.K) atomicOr(B.fault + r, kFaultCapacity);
+      B.cnt[(size_t)r * B.N + i] = min(count, K);
+      if (count > K) atomicOr(B.fault + r, kFaultCapacity);
     }
   }
 
