@@ -3,11 +3,14 @@
 // (include/libfly/neigh/list.hpp:138-154) and evaluating Spline::f/fp (spline.hpp:81-154).
 //
 // Two-pass, scatter-free gather. A sub-warp of G lanes owns one atom; each lane takes 16 / G consecutive
-// entries of every 16-entry round of the atom's neighbour row (one vector load), fetches each neighbour's
+// storage slots of every 16-slot round of the atom's neighbour row (one vector load), fetches each neighbour's
 // {x,y,z,F'} record with one 256-bit load, the spline knot {a,b,c,d} with one 256-bit read-only load, and the
 // partial sums are combined in a fixed, width-independent order (VirtSum). No atomics, no stores to other atoms.
-// These "row kernels" gather from global memory and work for every box; the tile kernels (tile.cuh) are the fast
-// path for fully periodic boxes and produce the same bits.
+// Rows are ordered by neighbour index and their rounds stored transposed (row_slot, device_common.cuh): the records one
+// warp-wide gather asks for are then 8 consecutive atoms x 4 consecutive neighbours, which is what the L1 data pipe --
+// the bound of these kernels -- serves cheapest.
+// These "row kernels" gather from global memory and work for every box; the tile kernels (tile.cuh, opt-in: measured
+// slower) stage cell windows in shared memory for fully periodic boxes and produce the same bits.
 //   pass 1: rho_b = sum_a phi_{a->b}(r);  F'_b = F_b'(rho_b) is stored in pos4[b].w   (eam.cpp:62-73)
 //   pass 2: grad_g = - sum_a [V'(r) + F'_g phi'_{a->g}(r) + F'_a phi'_{g->a}(r)] / r * dr (eam.cpp:90-107)
 // The FP64 pipe is the co-limiter of this path, so r and 1/r come from one rsqrt seed + one

@@ -18,8 +18,8 @@
 //                    round-to-nearest intrinsics (bit-exact neighbour sets), and compacts the hits
 //                    into the atom's row with warp ballots.
 //   6. order_rows    a warp per row sorts it by (neighbour index, shift) and stores it in the transposed
-//                    round layout of row_slot (device_common.cuh): the record gathers of the EAM passes
-//                    then fall into a few 128 B lines per load instruction.
+//                    round layout of row_slot (device_common.cuh): one gather instruction of the EAM passes
+//                    then asks for consecutive neighbours of consecutive atoms, often the same record twice.
 // All functions are written against one replica so that both the grid-wide kernels below and the
 // persistent search kernel (search.cuh) can call them.
 #pragma once
